@@ -1,0 +1,131 @@
+/* lievae.h -- C ABI of liblievae_sm100a.so (B200 / sm_100a kernels for the lie-vae SO(3) hot path).
+ *
+ * The reference (pimdh/lie-vae) has no FFI: its boundary is the Python surface of
+ * lie_vae/lie_tools.py, lie_vae/reparameterize.py and lie_vae/decoders.py.  Each entry point below
+ * replaces the ATen op chain behind one reference function (cited as file:line relative to the
+ * reference tree) and is what a maintainer binds from torch.autograd.Function wrappers (ctypes stub
+ * in INTEGRATION.md; lie_vae_b200/_cabi.py is that stub in this repo).
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers to dense row-major arrays, owned by the caller; outputs are
+ *     fully overwritten.  16-byte alignment gives the 128-bit fast path; unaligned spans fall back to
+ *     coalesced scalar accesses (never an error).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls only enqueue
+ *     work: no allocation, no synchronisation, no global mutable state; re-entrant per stream.
+ *   - Return value: 0 = success; < 0 = argument error (LV_ERR_*); > 0 = cudaError_t from the launch.
+ *     lv_last_error() returns the calling thread's message for the last non-zero return.
+ *   - `_f32` = float, `_f64` = double (same algorithm, all arithmetic in that type).
+ *   - Row counts n are int64; n = 0 is a no-op.
+ */
+#ifndef LIEVAE_H_
+#define LIEVAE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LV_OK 0
+#define LV_ERR_ARG (-1)          /* null pointer, negative size, workspace too small */
+#define LV_ERR_UNSUPPORTED (-2)  /* degree > 8, k > 64, too many channels */
+
+int lv_version(void);               /* major*10000 + minor*100 + patch */
+const char* lv_last_error(void);    /* thread-local, never NULL */
+int lv_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- so(3) <-> R^3: map_to_lie_algebra lie_tools.py:17-43, map_to_lie_vector lie_tools.py:46-53 ---- */
+int lv_hat_fwd_f32(const float* v /*n,3*/, float* X /*n,9*/, int64_t n, void* stream);
+int lv_hat_fwd_f64(const double* v, double* X, int64_t n, void* stream);
+int lv_hat_bwd_f32(const float* gX /*n,9*/, float* gv /*n,3*/, int64_t n, void* stream);
+int lv_hat_bwd_f64(const double* gX, double* gv, int64_t n, void* stream);
+int lv_vee_fwd_f32(const float* X /*n,9*/, float* v /*n,3*/, int64_t n, void* stream);
+int lv_vee_fwd_f64(const double* X, double* v, int64_t n, void* stream);
+int lv_vee_bwd_f32(const float* gv /*n,3*/, float* gX /*n,9*/, int64_t n, void* stream);
+int lv_vee_bwd_f64(const double* gv, double* gX, int64_t n, void* stream);
+
+/* ---- exponential map: rodrigues lie_tools.py:56-64.  v = 0 gives R = I (the reference gives NaN) ---- */
+int lv_rodrigues_fwd_f32(const float* v /*n,3*/, float* R /*n,9*/, int64_t n, void* stream);
+int lv_rodrigues_fwd_f64(const double* v, double* R, int64_t n, void* stream);
+int lv_rodrigues_bwd_f32(const float* v, const float* gR /*n,9*/, float* gv /*n,3*/, int64_t n, void* stream);
+int lv_rodrigues_bwd_f64(const double* v, const double* gR, double* gv, int64_t n, void* stream);
+
+/* ---- logarithm map: log_map lie_tools.py:100-109 (batched; output is the 3x3 algebra element) ---- */
+int lv_log_map_fwd_f32(const float* R /*n,9*/, float* X /*n,9*/, int64_t n, void* stream);
+int lv_log_map_fwd_f64(const double* R, double* X, int64_t n, void* stream);
+int lv_log_map_bwd_f32(const float* R, const float* gX, float* gR, int64_t n, void* stream);
+int lv_log_map_bwd_f64(const double* R, const double* gX, double* gR, int64_t n, void* stream);
+
+/* ---- quaternions (x,y,z,w scalar-last): quaternions_to_group_matrix lie_tools.py:183-192,
+ *      group_matrix_to_quaternions lie_tools.py:112-157 (Shepperd, argmax branch, 1e-6 eps) ---- */
+int lv_quat_to_mat_fwd_f32(const float* q /*n,4*/, float* R /*n,9*/, int64_t n, void* stream);
+int lv_quat_to_mat_fwd_f64(const double* q, double* R, int64_t n, void* stream);
+int lv_quat_to_mat_bwd_f32(const float* q, const float* gR, float* gq, int64_t n, void* stream);
+int lv_quat_to_mat_bwd_f64(const double* q, const double* gR, double* gq, int64_t n, void* stream);
+int lv_mat_to_quat_fwd_f32(const float* R /*n,9*/, float* q /*n,4*/, int64_t n, void* stream);
+int lv_mat_to_quat_fwd_f64(const double* R, double* q, int64_t n, void* stream);
+int lv_mat_to_quat_bwd_f32(const float* R, const float* gq, float* gR, int64_t n, void* stream);
+int lv_mat_to_quat_bwd_f64(const double* R, const double* gq, double* gR, int64_t n, void* stream);
+
+/* ---- ZYZ Euler angles: quaternions_to_eazyz lie_tools.py:160-175, group_matrix_to_eazyz
+ *      lie_tools.py:178-180 (fused: the quaternion stays in registers) ---- */
+int lv_quat_to_eazyz_fwd_f32(const float* q /*n,4*/, float* e /*n,3*/, int64_t n, void* stream);
+int lv_quat_to_eazyz_fwd_f64(const double* q, double* e, int64_t n, void* stream);
+int lv_quat_to_eazyz_bwd_f32(const float* q, const float* ge, float* gq, int64_t n, void* stream);
+int lv_quat_to_eazyz_bwd_f64(const double* q, const double* ge, double* gq, int64_t n, void* stream);
+int lv_mat_to_eazyz_fwd_f32(const float* R /*n,9*/, float* e /*n,3*/, int64_t n, void* stream);
+int lv_mat_to_eazyz_fwd_f64(const double* R, double* e, int64_t n, void* stream);
+int lv_mat_to_eazyz_bwd_f32(const float* R, const float* ge, float* gR, int64_t n, void* stream);
+int lv_mat_to_eazyz_bwd_f64(const double* R, const double* ge, double* gR, int64_t n, void* stream);
+
+/* ---- mean maps: s2s1rodrigues lie_tools.py:67-78 (s1 = (cos, sin)), s2s2_gram_schmidt
+ *      lie_tools.py:81-89 (rows e1, e2, e1 x e2), vector_to_eazyz lie_tools.py:92-97 ---- */
+int lv_s2s1_rodrigues_fwd_f32(const float* s2 /*n,3*/, const float* s1 /*n,2*/, float* R /*n,9*/, int64_t n, void* stream);
+int lv_s2s1_rodrigues_fwd_f64(const double* s2, const double* s1, double* R, int64_t n, void* stream);
+int lv_s2s1_rodrigues_bwd_f32(const float* s2, const float* s1, const float* gR, float* gs2, float* gs1, int64_t n, void* stream);
+int lv_s2s1_rodrigues_bwd_f64(const double* s2, const double* s1, const double* gR, double* gs2, double* gs1, int64_t n, void* stream);
+int lv_s2s2_gram_schmidt_fwd_f32(const float* v1 /*n,3*/, const float* v2 /*n,3*/, float* R /*n,9*/, int64_t n, void* stream);
+int lv_s2s2_gram_schmidt_fwd_f64(const double* v1, const double* v2, double* R, int64_t n, void* stream);
+int lv_s2s2_gram_schmidt_bwd_f32(const float* v1, const float* v2, const float* gR, float* gv1, float* gv2, int64_t n, void* stream);
+int lv_s2s2_gram_schmidt_bwd_f64(const double* v1, const double* v2, const double* gR, double* gv1, double* gv2, int64_t n, void* stream);
+int lv_vector_to_eazyz_fwd_f32(const float* v /*n,3*/, float* e /*n,3*/, int64_t n, void* stream);
+int lv_vector_to_eazyz_fwd_f64(const double* v, double* e, int64_t n, void* stream);
+int lv_vector_to_eazyz_bwd_f32(const float* v, const float* ge, float* gv, int64_t n, void* stream);
+int lv_vector_to_eazyz_bwd_f64(const double* v, const double* ge, double* gv, int64_t n, void* stream);
+
+/* ---- out[j] = sum_i in[i*inner + j]: reduces per-sample gradients over the n axis ---- */
+int lv_sum_leading_f32(const float* in, float* out, int64_t n, int64_t inner, void* stream);
+int lv_sum_leading_f64(const double* in, double* out, int64_t n, int64_t inner, void* stream);
+
+/* ---- fused SO(3) reparameterize + wrapped log-density.
+ *   N0reparameterize.nsample reparameterize.py:137-141 (v = eps*sigma, eps explicit),
+ *   SO3reparameterize.nsample reparameterize.py:269-273 (z = mu @ rodrigues(v)),
+ *   SO3reparameterize.log_posterior reparameterize.py:233-263 + utils.logsumexp utils.py:4-26.
+ *   mu (B,9), sigma (B,3) broadcast over n; eps (n,B,3); z (n,B,9); log_q (n,B) or NULL to skip.
+ *   Backward: gz (n,B,9) or NULL (=0), glq (n,B) or NULL (=0); writes PER-SAMPLE gradients
+ *   gmu (n,B,9), gsigma (n,B,3) -- for n > 1 reduce with lv_sum_leading_f32. ---- */
+int lv_so3_reparam_fwd_f32(const float* mu, const float* sigma, const float* eps, float* z, float* log_q,
+                           int64_t n, int64_t B, int k, void* stream);
+int lv_so3_reparam_bwd_f32(const float* mu, const float* sigma, const float* eps, const float* gz, const float* glq,
+                           float* gmu, float* gsigma, int64_t n, int64_t B, int k, void* stream);
+
+/* ---- block-diagonal Wigner-D action on a spectrum, degrees lmin..lmax (<= 8), C channels.
+ *   block_wigner_matrix_multiply lie_tools.py:226-253, wigner_d_matrix lie_tools.py:211-223,
+ *   _z_rot_mat lie_tools.py:195-208, ActionNet.forward decoders.py:47-56.
+ *   M = (lmax+1)^2 - lmin^2.  angles (N,3); out (N,M,C).
+ *   shared_spectrum != 0: spectrum is (M,C), the same for every sample (ActionNet.item_rep);
+ *   otherwise (N,M,C).  transpose != 0 applies D^T (lie_tools.py:249-250).
+ *   Backward: gout (N,M,C) -> gangles (N,3) and gspectrum ((M,C) summed over N if shared, else
+ *   (N,M,C)).  The shared case needs `workspace` of lv_wigner_bwd_workspace_floats(...) floats
+ *   (deterministic two-pass batch reduction, no atomics). ---- */
+int64_t lv_wigner_bwd_workspace_floats(int64_t N, int lmin, int lmax, int C);
+int lv_wigner_apply_fwd_f32(const float* angles, const float* spectrum, float* out, int64_t N, int lmin, int lmax,
+                            int C, int shared_spectrum, int transpose, void* stream);
+int lv_wigner_apply_bwd_f32(const float* angles, const float* spectrum, const float* gout, float* gangles,
+                            float* gspectrum, float* workspace, int64_t workspace_floats, int64_t N, int lmin,
+                            int lmax, int C, int shared_spectrum, int transpose, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIEVAE_H_ */

@@ -1,0 +1,218 @@
+"""torch.autograd.Function wrappers over the C ABI (include/lievae.h).
+
+These own allocation, shape / dtype / device checks and raise Python exceptions;
+the kernels behind them are hand-written sm_100a CUDA.  CPU tensors are rejected:
+this package has no CPU or eager-PyTorch fallback.
+"""
+import ctypes
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _cabi
+
+_SUFFIX = {torch.float32: "f32", torch.float64: "f64"}
+
+
+def _sfx(t):
+    try:
+        return _SUFFIX[t.dtype]
+    except KeyError:
+        raise TypeError("lie_vae_b200 kernels take float32 or float64 tensors, got %s" % t.dtype)
+
+
+def _require_cuda(*tensors):
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("lie_vae_b200 runs on CUDA tensors only (got a %s tensor); there is no CPU fallback"
+                               % t.device.type)
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError("tensors on different devices: %s vs %s" % (dev, t.device))
+    return dev
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _rows(t, width):
+    """(..., width...) -> contiguous (n, width) view/copy and the leading shape."""
+    return t.reshape(-1, width).contiguous()
+
+
+# ------------------------------------------------------------------------------ row ops
+def _make_row_op(name, in_shapes, out_shape, bwd_needs_inputs=True):
+    """Build a Function for an elementwise map with len(in_shapes) inputs and one output.
+
+    in_shapes / out_shape are the trailing per-sample shapes, e.g. (3,) -> (3, 3).
+    Entry points: lv_<name>_fwd_<sfx>(in..., out, n, stream),
+                  lv_<name>_bwd_<sfx>([in...,] gout, gin..., n, stream).
+    """
+    import math
+    in_w = [math.prod(s) for s in in_shapes]
+    out_w = math.prod(out_shape)
+
+    class _Op(Function):
+        @staticmethod
+        def forward(ctx, *inputs):
+            dev = _require_cuda(*inputs)
+            sfx = _sfx(inputs[0])
+            for t, s in zip(inputs, in_shapes):
+                if t.dtype != inputs[0].dtype:
+                    raise TypeError("%s: mixed dtypes" % name)
+                if tuple(t.shape[t.dim() - len(s):]) != tuple(s):
+                    raise ValueError("%s: expected trailing shape %s, got %s" % (name, tuple(s), tuple(t.shape)))
+            lead = inputs[0].shape[:inputs[0].dim() - len(in_shapes[0])]
+            flat = [_rows(t, w) for t, w in zip(inputs, in_w)]
+            n = flat[0].shape[0]
+            for f in flat:
+                if f.shape[0] != n:
+                    raise ValueError("%s: inputs disagree on the batch size" % name)
+            out = torch.empty((n, out_w), dtype=inputs[0].dtype, device=dev)
+            with torch.cuda.device(dev):
+                _cabi.call("lv_%s_fwd_%s" % (name, sfx), *[_cabi.ptr(f) for f in flat], _cabi.ptr(out), n, _stream())
+            ctx.save_for_backward(*(flat if bwd_needs_inputs else []))
+            ctx.meta = (sfx, n, lead, [t.shape for t in inputs])
+            return out.reshape(*lead, *out_shape)
+
+        @staticmethod
+        @once_differentiable
+        def backward(ctx, gout):
+            sfx, n, lead, shapes = ctx.meta
+            flat = list(ctx.saved_tensors)
+            g = gout.reshape(-1, out_w).contiguous()
+            dev = g.device
+            gins = [torch.empty((n, w), dtype=g.dtype, device=dev) for w in in_w]
+            with torch.cuda.device(dev):
+                _cabi.call("lv_%s_bwd_%s" % (name, sfx), *[_cabi.ptr(f) for f in flat], _cabi.ptr(g),
+                           *[_cabi.ptr(x) for x in gins], n, _stream())
+            return tuple(x.reshape(s) for x, s in zip(gins, shapes))
+
+    _Op.__name__ = "LV_" + name
+    return _Op
+
+
+Hat = _make_row_op("hat", [(3,)], (3, 3), bwd_needs_inputs=False)
+Vee = _make_row_op("vee", [(3, 3)], (3,), bwd_needs_inputs=False)
+Rodrigues = _make_row_op("rodrigues", [(3,)], (3, 3))
+LogMap = _make_row_op("log_map", [(3, 3)], (3, 3))
+QuatToMat = _make_row_op("quat_to_mat", [(4,)], (3, 3))
+MatToQuat = _make_row_op("mat_to_quat", [(3, 3)], (4,))
+QuatToEazyz = _make_row_op("quat_to_eazyz", [(4,)], (3,))
+MatToEazyz = _make_row_op("mat_to_eazyz", [(3, 3)], (3,))
+S2S1Rodrigues = _make_row_op("s2s1_rodrigues", [(3,), (2,)], (3, 3))
+S2S2GramSchmidt = _make_row_op("s2s2_gram_schmidt", [(3,), (3,)], (3, 3))
+VectorToEazyz = _make_row_op("vector_to_eazyz", [(3,)], (3,))
+
+
+def sum_leading(t):
+    """(n, ...) -> (...) summed over the first axis (gradient reduction over samples)."""
+    dev = _require_cuda(t)
+    n = t.shape[0]
+    if n == 1:
+        return t[0]
+    flat = t.reshape(n, -1).contiguous()
+    out = torch.empty(flat.shape[1], dtype=t.dtype, device=dev)
+    with torch.cuda.device(dev):
+        _cabi.call("lv_sum_leading_%s" % _sfx(t), _cabi.ptr(flat), _cabi.ptr(out), n, flat.shape[1], _stream())
+    return out.reshape(t.shape[1:])
+
+
+# ------------------------------------------------------------------------------ fused SO(3) reparameterize
+class SO3Reparam(Function):
+    """(mu (B,3,3), sigma (B,3), eps (n,B,3), k) -> z (n,B,3,3), log_q (n,B).   float32."""
+
+    @staticmethod
+    def forward(ctx, mu, sigma, eps, k):
+        dev = _require_cuda(mu, sigma, eps)
+        for t in (mu, sigma, eps):
+            if t.dtype != torch.float32:
+                raise TypeError("so3_reparameterize is float32 only, got %s" % t.dtype)
+        if mu.dim() != 3 or tuple(mu.shape[1:]) != (3, 3):
+            raise ValueError("mu must be (B,3,3), got %s" % (tuple(mu.shape),))
+        B = mu.shape[0]
+        if tuple(sigma.shape) != (B, 3):
+            raise ValueError("sigma must be (B,3), got %s" % (tuple(sigma.shape),))
+        if eps.dim() != 3 or tuple(eps.shape[1:]) != (B, 3):
+            raise ValueError("eps must be (n,B,3), got %s" % (tuple(eps.shape),))
+        n = eps.shape[0]
+        mu_c, sg_c, ep_c = mu.contiguous(), sigma.contiguous(), eps.contiguous()
+        z = torch.empty((n, B, 3, 3), dtype=torch.float32, device=dev)
+        log_q = torch.empty((n, B), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _cabi.call("lv_so3_reparam_fwd_f32", _cabi.ptr(mu_c), _cabi.ptr(sg_c), _cabi.ptr(ep_c), _cabi.ptr(z),
+                       _cabi.ptr(log_q), n, B, int(k), _stream())
+        ctx.save_for_backward(mu_c, sg_c, ep_c)
+        ctx.k = int(k)
+        return z, log_q
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gz, glq):
+        mu, sigma, eps = ctx.saved_tensors
+        n, B = eps.shape[0], eps.shape[1]
+        dev = mu.device
+        gz = None if gz is None else gz.contiguous()
+        glq = None if glq is None else glq.contiguous()
+        gmu = torch.empty((n, B, 3, 3), dtype=torch.float32, device=dev)
+        gsg = torch.empty((n, B, 3), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _cabi.call("lv_so3_reparam_bwd_f32", _cabi.ptr(mu), _cabi.ptr(sigma), _cabi.ptr(eps), _cabi.ptr(gz),
+                       _cabi.ptr(glq), _cabi.ptr(gmu), _cabi.ptr(gsg), n, B, ctx.k, _stream())
+        return sum_leading(gmu), sum_leading(gsg), None, None
+
+
+# ------------------------------------------------------------------------------ Wigner-D action
+class WignerApply(Function):
+    """angles (N,3), spectrum ((M,C) shared | (N,M,C)) -> (N,M,C), degrees lmin..lmax.   float32."""
+
+    @staticmethod
+    def forward(ctx, angles, spectrum, lmin, lmax, transpose):
+        dev = _require_cuda(angles, spectrum)
+        if angles.dtype != torch.float32 or spectrum.dtype != torch.float32:
+            raise TypeError("wigner apply is float32 only, got %s / %s" % (angles.dtype, spectrum.dtype))
+        if angles.dim() != 2 or angles.shape[1] != 3:
+            raise ValueError("angles must be (N,3)")
+        N = angles.shape[0]
+        M = (lmax + 1) ** 2 - lmin ** 2
+        shared = spectrum.dim() == 2
+        if shared:
+            if spectrum.shape[0] != M:
+                raise ValueError("spectrum must have %d rows for degrees %d..%d, got %s" % (M, lmin, lmax, tuple(spectrum.shape)))
+        elif spectrum.dim() != 3 or spectrum.shape[0] != N or spectrum.shape[1] != M:
+            raise ValueError("spectrum must be (N=%d, M=%d, C), got %s" % (N, M, tuple(spectrum.shape)))
+        C = spectrum.shape[-1]
+        a_c, s_c = angles.contiguous(), spectrum.contiguous()
+        out = torch.empty((N, M, C), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _cabi.call("lv_wigner_apply_fwd_f32", _cabi.ptr(a_c), _cabi.ptr(s_c), _cabi.ptr(out), N, lmin, lmax, C,
+                       int(shared), int(bool(transpose)), _stream())
+        ctx.save_for_backward(a_c, s_c)
+        ctx.meta = (N, lmin, lmax, C, shared, bool(transpose))
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        a_c, s_c = ctx.saved_tensors
+        N, lmin, lmax, C, shared, transpose = ctx.meta
+        dev = a_c.device
+        g = gout.contiguous()
+        gang = torch.empty((N, 3), dtype=torch.float32, device=dev)
+        gspec = torch.empty_like(s_c)
+        with torch.cuda.device(dev):
+            ws, nws = None, 0
+            if shared:
+                nws = _cabi.lib().lv_wigner_bwd_workspace_floats(N, lmin, lmax, C)
+                if nws < 0:
+                    raise RuntimeError("lv_wigner_bwd_workspace_floats: " + _cabi.last_error())
+                ws = torch.empty(max(nws, 1), dtype=torch.float32, device=dev)
+            _cabi.call("lv_wigner_apply_bwd_f32", _cabi.ptr(a_c), _cabi.ptr(s_c), _cabi.ptr(g), _cabi.ptr(gang),
+                       _cabi.ptr(gspec), _cabi.ptr(ws), nws, N, lmin, lmax, C, int(shared), int(transpose), _stream())
+        return gang, gspec, None, None, None

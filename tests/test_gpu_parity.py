@@ -1,0 +1,228 @@
+"""GPU parity: CUDA kernels (through the C ABI / autograd wrappers) vs the FP64 oracle and the
+reference-generated golden fixtures.  Run on the B200 box with ``-m gpu``.
+
+Tolerance (north_star): rtol 1e-5 (+ atol 1e-5) in FP32 against an FP64 evaluation.  For the two
+quantities where the reference's own FP32 code does not meet that bound against its FP64 self
+(log_q and d/dsigma, SURVEY.md App. C: cancellation in 2-2cos and clamp-edge flips) the rule is
+"at least as close to FP64 as the reference's FP32 arithmetic", checked by running the oracle in FP32.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import so3_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-5, 1e-5
+
+
+@pytest.fixture(scope="module")
+def lt():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import lie_vae_b200.lie_tools as m
+    return m
+
+
+def dev(a, dtype=torch.float32):
+    return torch.tensor(np.asarray(a), dtype=dtype, device="cuda")
+
+
+def close(actual, desired, rtol=RTOL, atol=ATOL, what=""):
+    a = actual.detach().double().cpu().numpy() if torch.is_tensor(actual) else np.asarray(actual)
+    d = desired.detach().double().cpu().numpy() if torch.is_tensor(desired) else np.asarray(desired)
+    np.testing.assert_allclose(a, d, rtol=rtol, atol=atol, err_msg=what)
+
+
+def frac_outside(a, d, rtol=RTOL, atol=ATOL):
+    a, d = np.asarray(a, dtype=np.float64), np.asarray(d, dtype=np.float64)
+    return float(np.mean(np.abs(a - d) > atol + rtol * np.abs(d)))
+
+
+def as_good_as_ref32(ours, ref64, ref32, what):
+    """ours (fp32 kernel) must be at least as close to the fp64 truth as the oracle run in fp32."""
+    ours = ours.detach().double().cpu().numpy()
+    ref64 = ref64.detach().double().cpu().numpy()
+    ref32 = ref32.detach().double().cpu().numpy()
+    f_ours, f_ref = frac_outside(ours, ref64), frac_outside(ref32, ref64)
+    e_ours, e_ref = np.abs(ours - ref64).max(), np.abs(ref32 - ref64).max()
+    assert f_ours <= f_ref + 1e-9 or f_ours == 0.0, "%s: %.3g of elements outside tol (reference fp32: %.3g)" % (what, f_ours, f_ref)
+    assert e_ours <= max(e_ref, 2e-5 * max(1.0, np.abs(ref64).max())), "%s: max abs err %.3g (reference fp32: %.3g)" % (what, e_ours, e_ref)
+
+
+def run_fn(fn, inputs, w, dtype):
+    leaves = [dev(x, dtype).requires_grad_(True) for x in inputs]
+    out = fn(*leaves)
+    (out * dev(w, dtype)).sum().backward()
+    return out, [l.grad for l in leaves]
+
+
+# ----------------------------------------------------------------------- elementwise family vs golden
+ROW_CASES = [
+    ("rodrigues", "rodrigues", ["v"], ["gv"]),
+    ("quat_to_mat", "quaternions_to_group_matrix", ["q"], ["gq"]),
+    ("mat_to_quat", "group_matrix_to_quaternions", ["R"], ["gR"]),
+    ("quat_to_eazyz", "quaternions_to_eazyz", ["q"], ["gq"]),
+    ("mat_to_eazyz", "group_matrix_to_eazyz", ["R"], ["gR"]),
+    ("s2s1", "s2s1rodrigues", ["s2", "s1"], ["gs2", "gs1"]),
+    ("s2s2", "s2s2_gram_schmidt", ["v1", "v2"], ["gv1", "gv2"]),
+    ("vector_to_eazyz", "vector_to_eazyz", ["v"], ["gv"]),
+    ("log_map", "log_map", ["R"], ["gR"]),
+]
+
+
+@pytest.mark.parametrize("fixture,fname,ins,gs", ROW_CASES)
+def test_rowop_f64_matches_reference(lt, fixture, fname, ins, gs):
+    g = load_golden(fixture)
+    out, grads = run_fn(getattr(lt, fname), [g[k] for k in ins], g["w"], torch.float64)
+    close(out, g["out"], 1e-9, 1e-10, fname)
+    for gr, k in zip(grads, gs):
+        close(gr, g[k], 1e-8, 1e-9, fname + " grad " + k)
+
+
+@pytest.mark.parametrize("fixture,fname,ins,gs", ROW_CASES)
+def test_rowop_f32_matches_reference(lt, fixture, fname, ins, gs):
+    g = load_golden(fixture)
+    out, grads = run_fn(getattr(lt, fname), [g[k] for k in ins], g["w"], torch.float32)
+    # fp32 reference arithmetic for the "as good as" rule
+    leaves = [torch.tensor(g[k], dtype=torch.float32).requires_grad_(True) for k in ins]
+    o32 = getattr(O, fname)(*leaves)
+    (o32 * torch.tensor(g["w"], dtype=torch.float32)).sum().backward()
+    as_good_as_ref32(out, torch.tensor(g["out"]), o32, fname)
+    for gr, k, leaf in zip(grads, gs, leaves):
+        as_good_as_ref32(gr, torch.tensor(g[k]), leaf.grad, fname + " grad " + k)
+
+
+def test_algebra_maps(lt):
+    g = load_golden("algebra")
+    for dt in (torch.float32, torch.float64):
+        v = dev(g["v"], dt).requires_grad_(True)
+        X = lt.map_to_lie_algebra(v)
+        close(X, g["hat"], 1e-7, 1e-7)
+        close(lt.map_to_lie_vector(X), g["vee"], 1e-7, 1e-7)
+        w = torch.randn_like(X)
+        (X * w).sum().backward()
+        vo = torch.tensor(g["v"]).requires_grad_(True)
+        (O.map_to_lie_algebra(vo) * w.double().cpu()).sum().backward()
+        close(v.grad, vo.grad, 1e-6, 1e-6)
+        Xl = dev(g["hat"], dt).requires_grad_(True)
+        wv = torch.randn(16, 3, device="cuda", dtype=dt)
+        (lt.map_to_lie_vector(Xl) * wv).sum().backward()
+        Xo = torch.tensor(g["hat"]).requires_grad_(True)
+        (O.map_to_lie_vector(Xo) * wv.double().cpu()).sum().backward()
+        close(Xl.grad, Xo.grad, 1e-6, 1e-6)
+
+
+def test_known_answers(lt):
+    R = lt.rodrigues(dev([[0.1, 0.2, 0.3]], torch.float64))
+    close(R[0], [[0.9357548033, -0.2831649606, 0.2101917060], [0.3029327134, 0.9505806179, -0.0680313164],
+                 [-0.1805400767, 0.1273345749, 0.9752903090]], 0, 1e-9)
+    close(lt.map_to_lie_vector(lt.log_map(R))[0], [0.1, 0.2, 0.3], 0, 1e-12)
+    M = lt.quaternions_to_group_matrix(dev([[0.1, 0.2, 0.3, 0.4]], torch.float64))
+    close(M[0], [[2 / 15, 14 / 15, -1 / 3], [-2 / 3, 1 / 3, 2 / 3], [11 / 15, 2 / 15, 2 / 3]], 0, 1e-12)
+    q = lt.group_matrix_to_quaternions(M)
+    close(q[0], [0.1825741430, 0.3651482861, 0.5477224291, 0.7302969145], 0, 1e-9)
+    close(lt.quaternions_to_eazyz(q)[0], [0.1798532748, 0.8410684190, 1.1071484928], 0, 1e-9)
+    close(lt.group_matrix_to_eazyz(R)[0], [2.5273197923, 0.2227639061, -2.8285702969], 0, 1e-9)
+    assert torch.equal(lt.rodrigues(torch.zeros(2, 3, device="cuda")), torch.eye(3, device="cuda").expand(2, 3, 3))
+
+
+# ----------------------------------------------------------------------- the reference's own property tests
+def test_log_exp_roundtrip(lt):
+    # lie_tools.py:281-291, scales 0.1 and 10 at 1e-6 in float64
+    torch.manual_seed(0)
+    for scale in (0.1, 10.0):
+        v0 = torch.randn(50, 3, dtype=torch.float64, device="cuda") * scale
+        R = lt.rodrigues(v0)
+        v = lt.map_to_lie_vector(lt.log_map(R))
+        Rp = lt.rodrigues(v)
+        vp = lt.map_to_lie_vector(lt.log_map(Rp))
+        close(Rp, R, 1e-6, 1e-6)
+        close(vp, v, 1e-6, 1e-6)
+
+
+def test_orthogonality_and_det(lt):
+    # lie_tools.py:396-425 at 1e-5 (fp32) / 1e-6 (fp64)
+    torch.manual_seed(0)
+    n = 10000
+    s2 = torch.nn.functional.normalize(torch.randn(n, 3, device="cuda"), dim=-1)
+    s1 = torch.nn.functional.normalize(torch.randn(n, 2, device="cuda"), dim=-1)
+    R = lt.s2s1rodrigues(s2, s1)
+    eye = torch.eye(3, device="cuda").expand(n, 3, 3)
+    close(R @ R.transpose(1, 2), eye, 1e-5, 1e-5)
+    close(torch.linalg.det(R), torch.ones(n), 1e-5, 1e-5)
+    v1, v2 = torch.rand(2, n, 3, dtype=torch.float64, device="cuda")
+    R = lt.s2s2_gram_schmidt(v1, v2)
+    close(R @ R.transpose(1, 2), eye.double(), 1e-6, 1e-6)
+    close(torch.linalg.det(R), torch.ones(n), 1e-6, 1e-6)
+    q = torch.randn(100000, 4, dtype=torch.float64, device="cuda")
+    R = lt.quaternions_to_group_matrix(q)
+    close(R @ R.transpose(1, 2), torch.eye(3).expand(100000, 3, 3), 0, 1e-6)
+    # mat -> quat -> mat round trip (lie_tools.py:301-304)
+    r = lt.random_group_matrices(10000, dtype=torch.float64, device="cuda")
+    close(lt.quaternions_to_group_matrix(lt.group_matrix_to_quaternions(r)), r, 1e-6, 1e-6)
+
+
+def test_eazyz_vs_scipy(lt):
+    # replaces the lie_learn KAT of lie_tools.py:294-320: R^T = Rz(a) Ry(b) Rz(c)  
+    from scipy.spatial.transform import Rotation
+    r = lt.random_group_matrices(2000, dtype=torch.float64, device="cuda")
+    ea = lt.group_matrix_to_eazyz(r).cpu().numpy()
+    back = Rotation.from_euler("ZYZ", ea).as_matrix()
+    np.testing.assert_allclose(back, r.cpu().numpy().transpose(0, 2, 1), atol=2e-5)
+
+
+# ----------------------------------------------------------------------- large seeded comparison vs the oracle
+@pytest.mark.parametrize("fname,shapes", [("rodrigues", [(3,)]), ("group_matrix_to_eazyz", None),
+                                          ("quaternions_to_group_matrix", [(4,)]), ("group_matrix_to_quaternions", None)])
+def test_rowop_large_vs_oracle(lt, fname, shapes):
+    torch.manual_seed(1)
+    n = 200003      # not a multiple of the tile
+    if shapes is None:
+        x = O.random_group_matrices(n, dtype=torch.float64)
+    else:
+        x = torch.randn(n, *shapes[0], dtype=torch.float64) * 1.3
+    xo = x.clone().requires_grad_(True)
+    out_o = getattr(O, fname)(xo)
+    w = torch.randn_like(out_o)
+    (out_o * w).sum().backward()
+    x32 = x.float().clone().requires_grad_(True)
+    o32 = getattr(O, fname)(x32)
+    (o32 * w.float()).sum().backward()
+    xg = x.float().cuda().requires_grad_(True)
+    out_g = getattr(lt, fname)(xg)
+    (out_g * w.float().cuda()).sum().backward()
+    as_good_as_ref32(out_g, out_o, o32, fname)
+    as_good_as_ref32(xg.grad, xo.grad, x32.grad, fname + " grad")
+
+
+def test_unaligned_and_noncontiguous_inputs(lt):
+    torch.manual_seed(2)
+    base = torch.randn(1001, 4, device="cuda")
+    v = base[1:, 1:]                      # non-contiguous, storage offset 5 floats
+    close(lt.rodrigues(v), O.rodrigues(v.double().cpu()), 1e-5, 1e-5)
+    flat = torch.randn(3 * 777 + 1, device="cuda")[1:].view(777, 3)     # contiguous but only 4-byte aligned
+    close(lt.rodrigues(flat), O.rodrigues(flat.double().cpu()), 1e-5, 1e-5)
+    assert lt.rodrigues(torch.empty(0, 3, device="cuda")).shape == (0, 3, 3)
+    close(lt.rodrigues(torch.randn(2, 5, 3, device="cuda")).shape, (2, 5, 3, 3), 0, 0)
+
+
+def test_errors(lt):
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        lt.rodrigues(torch.randn(4, 3))
+    with pytest.raises(TypeError):
+        lt.rodrigues(torch.randn(4, 3, device="cuda").half())
+    with pytest.raises(AssertionError):
+        lt.map_to_lie_algebra(torch.randn(4, 4, device="cuda"))
+    with pytest.raises(AssertionError):
+        lt.group_matrix_to_quaternions(torch.randn(4, 3, 2, device="cuda"))
+    with pytest.raises(AssertionError):
+        lt.quaternions_to_eazyz(torch.randn(4, 3, device="cuda"))
+    with pytest.raises(AssertionError):
+        lt.wigner_d_matrix(torch.randn(4, 2, device="cuda"), 1)
+    with pytest.raises(NotImplementedError):
+        lt.wigner_d_matrix(torch.randn(4, 3, device="cuda"), 9)

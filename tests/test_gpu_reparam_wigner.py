@@ -1,0 +1,293 @@
+"""GPU parity for the two hot kernels: fused SO(3) reparameterize(+log-density) and the Wigner-D action.
+
+CUDA (through the C ABI) vs golden fixtures from the unmodified reference, vs the FP64 oracle on
+seeded inputs, and size-independent properties at BASELINE.json's full sizes.  ``-m gpu``.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import so3_oracle as O
+from test_gpu_parity import RTOL, ATOL, as_good_as_ref32, close, dev
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import lie_vae_b200.lie_tools as lt
+    import lie_vae_b200.reparameterize as rp
+    import lie_vae_b200.decoders as dc
+    return lt, rp, dc
+
+
+# ----------------------------------------------------------------------- SO(3) reparameterize
+def oracle_reparam(mu, sigma, eps, k, wz, wl, dtype):
+    mu = torch.tensor(mu, dtype=dtype).requires_grad_(True)
+    sg = torch.tensor(sigma, dtype=dtype).requires_grad_(True)
+    z, lq = O.so3_reparameterize(mu, sg, torch.tensor(eps, dtype=dtype), k)
+    ((z * torch.tensor(wz, dtype=dtype)).sum() + (lq * torch.tensor(wl, dtype=dtype)).sum()).backward()
+    return z.detach(), lq.detach(), mu.grad, sg.grad
+
+
+@pytest.mark.parametrize("name", ["so3_reparam_k3", "so3_reparam_k10", "so3_reparam_n5", "so3_reparam_iwae",
+                                  "so3_reparam_ka6"])
+def test_reparam_matches_reference(mods, name):
+    _, rp, _ = mods
+    g = load_golden(name)
+    k = int(g["k"])
+    mu, sg = dev(g["mu"]).requires_grad_(True), dev(g["sigma"]).requires_grad_(True)
+    z, lq = rp.so3_reparameterize(mu, sg, dev(g["eps"]), k)
+    ((z * dev(g["wz"])).sum() + (lq * dev(g["wl"])).sum()).backward()
+    z32, lq32, gmu32, gsg32 = oracle_reparam(g["mu"], g["sigma"], g["eps"], k, g["wz"], g["wl"], torch.float32)
+    close(z, g["z"], RTOL, ATOL, "z")
+    close(mu.grad, g["gmu"], RTOL, ATOL, "g_mu")
+    as_good_as_ref32(lq, torch.tensor(g["log_q"]), lq32, "log_q")
+    as_good_as_ref32(sg.grad, torch.tensor(g["gsigma"]), gsg32, "g_sigma")
+
+
+@pytest.mark.parametrize("k", [3, 10, 1, 5, 0])
+def test_reparam_large_vs_oracle(mods, k):
+    _, rp, _ = mods
+    torch.manual_seed(0)
+    B = 100003
+    mu = O.random_group_matrices(B, dtype=torch.float64)
+    sigma = torch.nn.functional.softplus(torch.randn(B, 3, dtype=torch.float64))
+    sigma[: B // 4] = 0.02 + 2.48 * torch.rand(B // 4, 3, dtype=torch.float64)     # stress set U(0.02, 2.5)
+    eps = torch.randn(1, B, 3, dtype=torch.float64)
+    wz, wl = torch.randn(1, B, 3, 3, dtype=torch.float64), torch.randn(1, B, dtype=torch.float64)
+    z64, lq64, gmu64, gsg64 = oracle_reparam(mu, sigma, eps, k, wz, wl, torch.float64)
+    z32, lq32, gmu32, gsg32 = oracle_reparam(mu, sigma, eps, k, wz, wl, torch.float32)
+    mug, sgg = mu.float().cuda().requires_grad_(True), sigma.float().cuda().requires_grad_(True)
+    z, lq = rp.so3_reparameterize(mug, sgg, eps.float().cuda(), k)
+    ((z * wz.float().cuda()).sum() + (lq * wl.float().cuda()).sum()).backward()
+    close(z, z64, RTOL, ATOL, "z")
+    as_good_as_ref32(mug.grad, gmu64, gmu32, "g_mu")
+    as_good_as_ref32(lq, lq64, lq32, "log_q")
+    as_good_as_ref32(sgg.grad, gsg64, gsg32, "g_sigma")
+
+
+def test_reparam_multisample_broadcast(mods):
+    # n > 1 with B not a multiple of anything: tiles wrap over the broadcast mu / sigma rows
+    _, rp, _ = mods
+    torch.manual_seed(3)
+    n, B, k = 7, 333, 3
+    mu = O.random_group_matrices(B, dtype=torch.float64)
+    sigma = torch.nn.functional.softplus(torch.randn(B, 3, dtype=torch.float64))
+    eps = torch.randn(n, B, 3, dtype=torch.float64)
+    wz, wl = torch.randn(n, B, 3, 3, dtype=torch.float64), torch.randn(n, B, dtype=torch.float64)
+    z64, lq64, gmu64, gsg64 = oracle_reparam(mu, sigma, eps, k, wz, wl, torch.float64)
+    _, lq32, gmu32, gsg32 = oracle_reparam(mu, sigma, eps, k, wz, wl, torch.float32)
+    mug, sgg = mu.float().cuda().requires_grad_(True), sigma.float().cuda().requires_grad_(True)
+    z, lq = rp.so3_reparameterize(mug, sgg, eps.float().cuda(), k)
+    assert z.shape == (n, B, 3, 3) and lq.shape == (n, B)
+    ((z * wz.float().cuda()).sum() + (lq * wl.float().cuda()).sum()).backward()
+    close(z, z64, RTOL, ATOL)
+    as_good_as_ref32(mug.grad, gmu64, gmu32, "g_mu")
+    as_good_as_ref32(lq, lq64, lq32, "log_q")
+    as_good_as_ref32(sgg.grad, gsg64, gsg32, "g_sigma")
+
+
+def test_reparam_full_size_properties(mods):
+    # BASELINE config 2: B = 2^20.  z orthogonal with det 1; log_q finite; z^T mu^T = exp(-v)
+    lt, rp, _ = mods
+    torch.manual_seed(0)
+    B = 1 << 20
+    mu = lt.random_group_matrices(B, device="cuda")
+    sigma = torch.nn.functional.softplus(torch.randn(B, 3, device="cuda"))
+    eps = torch.randn(1, B, 3, device="cuda")
+    z, lq = rp.so3_reparameterize(mu, sigma, eps, 3)
+    eye = torch.eye(3, device="cuda")
+    assert (z[0] @ z[0].transpose(1, 2) - eye).abs().max().item() < 5e-6
+    assert (torch.linalg.det(z[0]) - 1).abs().max().item() < 5e-6
+    assert torch.isfinite(lq).all()
+    # mu^T z = exp(v): recover v with the log map where it is well conditioned
+    v = (eps * sigma)[0]
+    theta = v.norm(dim=-1)
+    ok = (theta > 0.1) & (theta < 3.0)
+    rel = mu.transpose(1, 2) @ z[0]
+    v_back = lt.map_to_lie_vector(lt.log_map(rel))
+    assert (v_back[ok] - v[ok]).abs().max().item() < 2e-4
+    # log_q is invariant to the mean
+    _, lq2 = rp.so3_reparameterize(lt.random_group_matrices(B, device="cuda"), sigma, eps, 3)
+    assert torch.equal(lq, lq2)
+
+
+def test_module_api(mods):
+    lt, rp, _ = mods
+    torch.manual_seed(0)
+    m = rp.SO3reparameterize(rp.N0reparameterize(10, 3), rp.AlgebraMean(10), k=3).cuda()
+    x = torch.randn(64, 10, device="cuda")
+    z = m(x, n=4)
+    assert z.shape == (4, 64, 3, 3)
+    lq, lp, kl = m.log_posterior(), m.log_prior(), m.kl()
+    assert lq.shape == (4, 64) and lq.dtype == torch.float32
+    assert lp.shape == (4, 64) and lp.dtype == torch.float64 and abs(lp[0, 0].item() + 4.368901313378636) < 1e-12
+    assert kl.shape == (64,) and kl.dtype == torch.float64
+    # same numbers as the oracle fed with the module's own mu / sigma / eps
+    zo, lqo = O.so3_reparameterize(m.mu_lie.double().cpu(), m.reparameterize.sigma.double().cpu(),
+                                   m.reparameterize.eps.double().cpu(), 3)
+    close(z, zo, RTOL, ATOL)
+    close(lq, lqo, 1e-4, 1e-4)
+    close(m.v, m.reparameterize.eps * m.reparameterize.sigma, 0, 0)
+    (kl.sum() + z.sum()).backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+    assert sorted(m.state_dict().keys()) == ["mean_module.map.bias", "mean_module.map.weight",
+                                            "reparameterize.sigma_linear.bias", "reparameterize.sigma_linear.weight"]
+    for mean in (rp.QuaternionMean(10), rp.S2S1Mean(10), rp.S2S2Mean(10)):
+        mm = rp.SO3reparameterize(rp.N0reparameterize(10, 3, fixed_sigma=0.3), mean.cuda(), k=10).cuda()
+        zz = mm(x)
+        assert (zz[0] @ zz[0].transpose(1, 2) - torch.eye(3, device="cuda")).abs().max().item() < 1e-5
+        mm.kl().sum().backward()
+    m.deterministic()
+    assert torch.equal(m(x, n=2)[1], m.mu_lie)
+
+
+# ----------------------------------------------------------------------- Wigner
+def test_wigner_d_matches_reference(mods):
+    lt, _, _ = mods
+    g = load_golden("wigner_d")
+    ang = dev(g["angles"])
+    for l in range(9):
+        close(lt.wigner_d_matrix(ang, l), g["D%d" % l], RTOL, ATOL, "D%d" % l)
+
+
+@pytest.mark.parametrize("tag", ["L8C3", "L3C1", "L5C10"])
+@pytest.mark.parametrize("tr", ["N", "T"])
+def test_block_wigner_matches_reference(mods, tag, tr):
+    lt, _, _ = mods
+    g = load_golden("block_wigner_%s_%s" % (tag, tr))
+    L = int(g["max_degree"])
+    a, s = dev(g["angles"]).requires_grad_(True), dev(g["spectrum"]).requires_grad_(True)
+    out = lt.block_wigner_matrix_multiply(a, s, L, transpose=(tr == "T"))
+    (out * dev(g["w"])).sum().backward()
+    close(out, g["out"], RTOL, ATOL)
+    close(s.grad, g["gspectrum"], RTOL, ATOL)
+    close(a.grad, g["gangles"], 2e-5, 2e-5)
+
+
+@pytest.mark.parametrize("name", ["action_net_L8C10", "action_net_L3C3"])
+def test_action_net_matches_reference(mods, name):
+    _, _, dc = mods
+    g = load_golden(name)
+    L, tr = int(g["degrees"]), bool(int(g["transpose"]))
+    C = g["item_rep"].shape[1]
+    net = dc.ActionNet(L, torch.nn.Sequential(), rep_copies=C, transpose=tr).cuda()
+    net.item_rep.data = dev(g["item_rep"])
+    a = dev(g["angles"]).requires_grad_(True)
+    out = net(a)
+    (out * dev(g["w"])).sum().backward()
+    close(out, g["out"], RTOL, ATOL)
+    close(net.item_rep.grad, g["gitem"], RTOL, 2e-5)
+    close(a.grad, g["gangles"], 2e-5, 5e-5)
+
+
+@pytest.mark.parametrize("L,C,N,tr", [(8, 10, 4099, False), (8, 10, 1000, True), (6, 10, 2048, False), (3, 3, 777, False),
+                                      (8, 1, 513, False), (2, 32, 300, True), (0, 4, 65, False)])
+def test_action_net_vs_oracle(mods, L, C, N, tr):
+    _, _, dc = mods
+    torch.manual_seed(L * 100 + C)
+    M = (L + 1) ** 2
+    ang = O.group_matrix_to_eazyz(O.random_group_matrices(N, dtype=torch.float64))
+    item = torch.randn(M, C, dtype=torch.float64)
+    w = torch.randn(N, M * C, dtype=torch.float64)
+
+    def run_oracle(dt):
+        a, it = ang.to(dt).requires_grad_(True), item.to(dt).requires_grad_(True)
+        out = O.action_net_forward(a, it, L, tr)
+        (out * w.to(dt)).sum().backward()
+        return out.detach(), a.grad, it.grad
+    o64, ga64, gi64 = run_oracle(torch.float64)
+    o32, ga32, gi32 = run_oracle(torch.float32)
+    net = dc.ActionNet(L, torch.nn.Sequential(), rep_copies=C, transpose=tr).cuda()
+    net.item_rep.data = item.float().cuda()
+    a = ang.float().cuda().requires_grad_(True)
+    out = net(a)
+    (out * w.float().cuda()).sum().backward()
+    as_good_as_ref32(out, o64, o32, "out")
+    as_good_as_ref32(a.grad, ga64, ga32, "g_angles")
+    # the batch-summed gradient: relative to its own scale (sum of N terms)
+    scale = gi64.abs().max().item()
+    assert (net.item_rep.grad.double().cpu() - gi64).abs().max().item() <= max((gi32.double() - gi64).abs().max().item(), 2e-6 * scale)
+
+
+def test_wigner_reference_properties(mods):
+    # lie_tools.py:337-357: orthogonality, W(g)W(g^-1) = I, W(b)W(a) = W(ab) (rtol/atol 1e-3 in the reference)
+    lt, _, _ = mods
+    torch.manual_seed(0)
+    for l in range(9):
+        r = lt.random_group_matrices(2000, device="cuda")
+        D = lt.wigner_d_matrix(lt.group_matrix_to_eazyz(r), l)
+        eye = torch.eye(2 * l + 1, device="cuda").expand_as(D)
+        close(D @ D.transpose(1, 2), eye, 1e-4, 1e-5)
+        Dinv = lt.wigner_d_matrix(lt.group_matrix_to_eazyz(r.transpose(1, 2)), l)
+        close(D @ Dinv, eye, 1e-4, 2e-5)
+        ra, rb = lt.random_group_matrices(2000, device="cuda"), lt.random_group_matrices(2000, device="cuda")
+        wa = lt.wigner_d_matrix(lt.group_matrix_to_eazyz(ra), l)
+        wb = lt.wigner_d_matrix(lt.group_matrix_to_eazyz(rb), l)
+        wc = lt.wigner_d_matrix(lt.group_matrix_to_eazyz(ra.bmm(rb)), l)
+        close(wb.bmm(wa), wc, 1e-3, 1e-3)
+    # l = 1 block is the rotation itself in the (y,z,x) basis: D1(eazyz(R)) = P R^T P^T
+    r = lt.random_group_matrices(100, device="cuda")
+    D1 = lt.wigner_d_matrix(lt.group_matrix_to_eazyz(r), 1)
+    P = torch.tensor([[0., 1, 0], [0, 0, 1], [1, 0, 0]], device="cuda")
+    close(D1, P @ r.transpose(1, 2) @ P.t(), 1e-5, 2e-6)
+
+
+def test_wigner_full_size_properties(mods):
+    # BASELINE config 3: N = 65536, L = 8, C = 10.  D is orthogonal: per-degree norms are preserved;
+    # D^T D = I through the transpose flag; linear in the spectrum; shared == expanded per-sample.
+    lt, _, dc = mods
+    torch.manual_seed(0)
+    N, L, C = 65536, 8, 10
+    M = (L + 1) ** 2
+    ang = lt.group_matrix_to_eazyz(lt.random_group_matrices(N, device="cuda"))
+    item = torch.randn(M, C, device="cuda")
+    out = lt.block_wigner_matrix_multiply(ang, item.expand(N, -1, -1), L)
+    assert out.shape == (N, M, C)
+    start = 0
+    for l in range(L + 1):
+        d = 2 * l + 1
+        n_in = item[start:start + d].pow(2).sum(0)
+        n_out = out[:, start:start + d].pow(2).sum(1)
+        assert ((n_out - n_in) / n_in).abs().max().item() < 2e-5
+        start += d
+    back = lt.block_wigner_matrix_multiply(ang, out, L, transpose=True)
+    assert (back - item).abs().max().item() < 2e-5
+    sub = slice(0, 4096)
+    per_sample = lt.block_wigner_matrix_multiply(ang[sub], item.expand(4096, -1, -1).contiguous(), L)
+    assert torch.equal(per_sample, out[sub])
+    other = torch.randn(M, C, device="cuda")
+    lin = lt.block_wigner_matrix_multiply(ang[sub], (2 * item - 3 * other).expand(4096, -1, -1), L)
+    ref = 2 * out[sub] - 3 * lt.block_wigner_matrix_multiply(ang[sub], other.expand(4096, -1, -1), L)
+    assert (lin - ref).abs().max().item() < 5e-5
+    # backward: deterministic, and grad(item_rep) of sum(out * g) equals sum_n D_n^T g_n
+    net = dc.ActionNet(L, torch.nn.Sequential(), rep_copies=C).cuda()
+    net.item_rep.data = item
+    g = torch.randn(N, M * C, device="cuda")
+    a = ang.clone().requires_grad_(True)
+    (net(a) * g).sum().backward()
+    g1 = net.item_rep.grad.clone()
+    net.item_rep.grad = None
+    a2 = ang.clone().requires_grad_(True)
+    (net(a2) * g).sum().backward()
+    assert torch.equal(g1, net.item_rep.grad) and torch.equal(a.grad, a2.grad)
+    gt = lt.block_wigner_matrix_multiply(ang, g.view(N, M, C), L, transpose=True).double().sum(0)
+    assert (g1.double() - gt).abs().max().item() < 1e-3 * gt.abs().max().item()
+
+
+def test_wigner_errors(mods):
+    lt, _, dc = mods
+    a = torch.randn(4, 3, device="cuda")
+    with pytest.raises(NotImplementedError):
+        lt.block_wigner_matrix_multiply(a, torch.randn(4, 100, 2, device="cuda"), 9)
+    with pytest.raises(ValueError):
+        lt.block_wigner_matrix_multiply(a, torch.randn(4, 10, 2, device="cuda"), 2)
+    with pytest.raises(AssertionError):
+        dc.ActionNet(2, torch.nn.Sequential()).cuda()(torch.randn(4, 4, device="cuda"))
+    assert lt.block_wigner_matrix_multiply(torch.empty(0, 3, device="cuda"), torch.empty(0, 9, 2, device="cuda"), 2).shape == (0, 9, 2)
