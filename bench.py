@@ -203,15 +203,17 @@ def run_ours(args):
     g_sigma = torch.empty(n_loc, 3, device=dev)
     g_item = torch.zeros(M, CHANNELS, device=dev)
     red = torch.zeros(1 + M * CHANNELS, device=dev)
-    step_obj = FusedSO3ActionStep(micro, L_MAX, CHANNELS, K_WIND, device=dev)
+    step_obj = FusedSO3ActionStep(n_loc, micro, L_MAX, CHANNELS, K_WIND, device=dev)
 
     def one_step():
         g_item.zero_()
+        step_obj.latent_forward(mu, sigma, eps, log_q)
         for i in range(n_micro):
-            sl = slice(i * micro, (i + 1) * micro)
-            step_obj.forward(mu[sl], sigma[sl], eps[sl], item, y[i % 2], log_q[sl])
-            step_obj.backward(mu[sl], sigma[sl], eps[sl], item, gy[i % NBUF], glq[sl], g_mu[sl], g_sigma[sl])
+            lo, hi = i * micro, (i + 1) * micro
+            step_obj.decode_forward(lo, hi, item, y[i % 2])
+            step_obj.decode_backward(lo, hi, item, gy[i % NBUF])
             g_item.add_(step_obj.g_item)
+        step_obj.latent_backward(mu, sigma, eps, glq, g_mu, g_sigma)
         # loss = sum(y * g_y) + sum(log_q * g_lq);  y is linear in item_rep, so sum(y * g_y) = <item_rep, grad item_rep>
         red[0] = (item * g_item).sum() + torch.dot(log_q, glq)
         red[1:] = g_item.view(-1)
@@ -321,8 +323,10 @@ def run_ours(args):
         kernels = {}
         for k in KERNELS:
             avg_ms = sum(kern_ms[k]) / len(kern_ms[k])
-            gbs = abytes[k] * micro / (avg_ms * 1e-3) / 1e9
-            kernels[k] = {"avg_ms": round(avg_ms, 4), "bytes_per_sample": abytes[k], "gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
+            per_launch = micro if k.startswith("wigner") else n_loc
+            gbs = abytes[k] * per_launch / (avg_ms * 1e-3) / 1e9
+            kernels[k] = {"avg_ms": round(avg_ms, 4), "samples_per_launch": per_launch, "bytes_per_sample": abytes[k],
+                          "gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
         dom = "wigner_bwd"
         fused_bytes = sum(abytes.values()) - (36 + 36) - (12 + 12) - (12 + 12) - (36 + 36)   # minus z, angles, g_angles, g_z round trips
         line = {
@@ -334,7 +338,7 @@ def run_ours(args):
             "e2e": {"value": samples_per_step / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": n_loc * 60, "d2h_bytes_per_step": 4 * (1 + M * CHANNELS),
                     "api": "so3_reparameterize -> group_matrix_to_eazyz -> WignerApply (autograd), pinned host mu/sigma/eps, double-buffered copies"},
-            "gpu_launches": step_obj.LAUNCHES_PER_MICROBATCH * n_micro * args.steps,
+            "gpu_launches": (step_obj.LAUNCHES_PER_MICROBATCH * n_micro + step_obj.LAUNCHES_PER_SHARD) * args.steps,
             "roofline": {"bound": "hbm", "kernel": "wigner_bwd_kernel<shared>", "achieved": kernels[dom]["gbs"], "peak": peak,
                          "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": abytes[dom] * micro},

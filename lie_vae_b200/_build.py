@@ -26,17 +26,34 @@ def is_stale():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
+def _compile_one(args):
+    src, obj, verbose = args
+    cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+    proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    return src, proc.returncode, proc.stdout + proc.stderr
+
+
 def build(force=False, verbose=False):
-    """Compile every CUDA source into lie_vae_b200/liblievae_sm100a.so.  Returns the path."""
+    """Compile every CUDA source (in parallel, one object per file) and link lie_vae_b200/liblievae_sm100a.so."""
     if not force and not is_stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
-    proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    jobs = [(s, os.path.join(objdir, s.replace(".cu", ".o")), verbose) for s in SOURCES]
+    with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
+        results = list(ex.map(_compile_one, jobs))
+    for src, rc, log in results:
+        if rc != 0:
+            sys.stderr.write(log[-12000:])
+            raise RuntimeError("nvcc failed compiling %s" % src)
+        if verbose:
+            sys.stderr.write("==== %s\n%s" % (src, log))
+    link = [_nvcc(), "-shared", "-o", LIB] + [j[1] for j in jobs]
+    proc = subprocess.run(link, cwd=CSRC, capture_output=True, text=True)
     if proc.returncode != 0:
         sys.stderr.write(proc.stdout[-4000:] + proc.stderr[-8000:])
-        raise RuntimeError("nvcc failed building %s" % LIB)
-    if verbose:
-        sys.stderr.write(proc.stderr)
+        raise RuntimeError("nvcc failed linking %s" % LIB)
     return LIB
 
 

@@ -52,18 +52,37 @@ template <> struct Sc<double> {
 // A CTA owns `rows` consecutive rows of W scalars; the tile is one contiguous
 // span of global memory, copied with 16-byte accesses when the span start is
 // 16-byte aligned and scalar (still fully coalesced) accesses otherwise.
+// Asynchronous global->shared tile copy (cp.async / LDGSTS): every thread puts ALL of its pieces in
+// flight before anyone waits, so a CTA has its whole tile outstanding at once (a load->store loop
+// through registers keeps only a few 16-byte requests per thread in flight and is latency-bound).
+// 16-byte pieces bypass L1 (.cg: each byte is used once); spans that are not 16-byte aligned fall
+// back to 4-byte pieces (.ca), still asynchronous and fully coalesced.
+// Complete with tile_async_wait() followed by __syncthreads().
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(uint32_t(__cvta_generic_to_shared(smem_dst))), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(uint32_t(__cvta_generic_to_shared(smem_dst))), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void tile_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 template <typename T>
 __device__ __forceinline__ void tile_g2s(T* __restrict__ dst, const T* __restrict__ src, int count) {
+    static_assert(sizeof(T) == 4 || sizeof(T) == 8, "4- or 8-byte scalars");
     constexpr int V = 16 / sizeof(T);
     const int tid = threadIdx.x, nt = blockDim.x;
     if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
         const int nv = count / V;
-        const int4* s4 = reinterpret_cast<const int4*>(src);
-        int4* d4 = reinterpret_cast<int4*>(dst);
-        for (int i = tid; i < nv; i += nt) d4[i] = __ldg(s4 + i);
-        for (int i = nv * V + tid; i < count; i += nt) dst[i] = __ldg(src + i);
+        for (int i = tid; i < nv; i += nt) cp_async16(dst + i * V, src + i * V);
+        const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src + nv * V);
+        uint32_t* d32 = reinterpret_cast<uint32_t*>(dst + nv * V);
+        const int rest = (count - nv * V) * int(sizeof(T) / 4);
+        for (int i = tid; i < rest; i += nt) cp_async4(d32 + i, s32 + i);
     } else {
-        for (int i = tid; i < count; i += nt) dst[i] = __ldg(src + i);
+        const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
+        uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+        const int n32 = count * int(sizeof(T) / 4);
+        for (int i = tid; i < n32; i += nt) cp_async4(d32 + i, s32 + i);
     }
 }
 
@@ -300,11 +319,14 @@ __device__ __forceinline__ void quat_to_eazyz_bwd(const T* q, const T* ge, T* gq
     const T lo = T(-1.0 + 1e-6), hi = T(1.0 - 1e-6);
     // alpha = atan2(ya, xa)
     const T ya = q[1] * q[2] - q[0] * q[3], xa = q[0] * q[2] + q[1] * q[3];
-    const T ra = ge[0] / (xa * xa + ya * ya);
+    // torch's atan2 backward zeroes the reciprocal at the origin (x = y = 0)
+    const T da = xa * xa + ya * ya;
+    const T ra = da > T(0) ? ge[0] / da : T(0);
     const T gya = xa * ra, gxa = -ya * ra;
     // gamma = atan2(yc, xc)
     const T yc = q[0] * q[3] + q[1] * q[2], xc = q[1] * q[3] - q[0] * q[2];
-    const T rc = ge[2] / (xc * xc + yc * yc);
+    const T dc = xc * xc + yc * yc;
+    const T rc = dc > T(0) ? ge[2] / dc : T(0);
     const T gyc = xc * rc, gxc = -yc * rc;
     // beta = acos(clamp(w)); clamp passes gradient on the closed interval
     const T w = q[3] * q[3] - q[0] * q[0] - q[1] * q[1] + q[2] * q[2];

@@ -75,6 +75,7 @@ row_kernel(const T* __restrict__ g0, const T* __restrict__ g1, const T* __restri
     if constexpr (Op::I0 > 0) tile_g2s(s0, g0 + row0 * Op::I0, rows * Op::I0);
     if constexpr (Op::I1 > 0) tile_g2s(s1, g1 + row0 * Op::I1, rows * Op::I1);
     if constexpr (Op::I2 > 0) tile_g2s(s2, g2 + row0 * Op::I2, rows * Op::I2);
+    tile_async_wait();
     __syncthreads();
     const int t = threadIdx.x;
     if (t < rows) {

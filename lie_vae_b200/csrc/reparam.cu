@@ -145,6 +145,7 @@ so3_reparam_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ s
     stage_bcast<9>(s_m, mu, i0, rows, B);
     stage_bcast<3>(s_s, sigma, i0, rows, B);
     tile_g2s(s_e, eps + i0 * 3, rows * 3);
+    tile_async_wait();
     __syncthreads();
     const int t = threadIdx.x;
     if (t < rows) {
@@ -192,6 +193,7 @@ so3_reparam_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ s
     stage_bcast<3>(s_s, sigma, i0, rows, B);
     tile_g2s(s_e, eps + i0 * 3, rows * 3);
     if (gz != nullptr) tile_g2s(s_g, gz + i0 * 9, rows * 9);
+    tile_async_wait();
     __syncthreads();
     const int t = threadIdx.x;
     if (t < rows) {

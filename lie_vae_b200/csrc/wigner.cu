@@ -12,7 +12,9 @@
 // lives in registers.  cos/sin(m*angle), m = 1..8, are computed once per sample by three threads
 // (sincosf + angle-addition recurrence) and shared through smem.  The CTA's (S, M, C) output tile
 // is contiguous in global memory: it is assembled in shared memory and moved with 128-bit
-// coalesced accesses.
+// coalesced accesses.  The channel count is a template parameter for the common cases so that
+// every tile / spectrum access is base + immediate (no per-access integer math); CT = 0 is the
+// run-time-C fallback.
 //
 // Backward (hand-derived; G = d/dphi X(phi) X(phi)^-1 is the pair generator
 // (G w)_i = (l-i) w_{2l-i}):
@@ -37,25 +39,26 @@ constexpr int WG_MAX_THREADS = 256;
 using wg::jmul;
 
 // pair rotations: x <- X(phi) x          (lie_tools.py:195-208: X[i,i]=cos((l-i)phi), X[i,2l-i]=sin((l-i)phi))
-template <int L>
+// cs[m-1] = (cos m phi, sin m phi); two frequencies per 128-bit LDS.  TRANSPOSED: X(phi)^T = X(-phi).
+template <int L, bool TRANSPOSED>
 __device__ __forceinline__ void xrot(float (&x)[2 * L + 1], const float2* __restrict__ cs) {
+    const float4* cs4 = reinterpret_cast<const float4*>(cs);
 #pragma unroll
-    for (int m = 1; m <= L; ++m) {
-        const float2 t = cs[m - 1];
-        const float a = x[L - m], b = x[L + m];
-        x[L - m] = fmaf(t.x, a, t.y * b);
-        x[L + m] = fmaf(t.x, b, -(t.y * a));
-    }
-}
-// x <- X(phi)^T x = X(-phi) x
-template <int L>
-__device__ __forceinline__ void xrot_t(float (&x)[2 * L + 1], const float2* __restrict__ cs) {
-#pragma unroll
-    for (int m = 1; m <= L; ++m) {
-        const float2 t = cs[m - 1];
-        const float a = x[L - m], b = x[L + m];
-        x[L - m] = fmaf(t.x, a, -(t.y * b));
-        x[L + m] = fmaf(t.x, b, t.y * a);
+    for (int p = 0; p < (L + 1) / 2; ++p) {
+        float4 t = cs4[p];
+        if (TRANSPOSED) { t.y = -t.y; t.w = -t.w; }
+        {
+            const int m = 2 * p + 1;
+            const float a = x[L - m], b = x[L + m];
+            x[L - m] = fmaf(t.x, a, t.y * b);
+            x[L + m] = fmaf(t.x, b, -(t.y * a));
+        }
+        if (2 * p + 2 <= L) {
+            const int m = 2 * p + 2;
+            const float a = x[L - m], b = x[L + m];
+            x[L - m] = fmaf(t.z, a, t.w * b);
+            x[L + m] = fmaf(t.z, b, -(t.w * a));
+        }
     }
 }
 // <h, G w> = sum_m m (h[l-m] w[l+m] - h[l+m] w[l-m])
@@ -95,40 +98,39 @@ __device__ __forceinline__ void load_col(float (&x)[2 * L + 1], const float* __r
 }
 
 template <int L, bool GLOBAL_SRC>
-__device__ __forceinline__ void degree_fwd(const float* __restrict__ src, float* __restrict__ dst, int C,
-                                           const float2* __restrict__ tg) {
+__device__ __forceinline__ void degree_fwd(const float* src, float* dst, int C, const float2* __restrict__ tg) {
     float x[2 * L + 1], y[2 * L + 1];
     load_col<L, GLOBAL_SRC>(x, src, C);
-    xrot<L>(x, tg + 2 * WG_LMAX);
+    xrot<L, false>(x, tg + 2 * WG_LMAX);
     jmul<L>(x, y);
-    xrot<L>(y, tg + WG_LMAX);
+    xrot<L, false>(y, tg + WG_LMAX);
     jmul<L>(y, x);
-    xrot<L>(x, tg);
+    xrot<L, false>(x, tg);
 #pragma unroll
     for (int i = 0; i < 2 * L + 1; ++i) dst[i * C] = x[i];
 }
 
 // g (smem tile column): upstream gradient in, spectrum gradient out (in place).
-template <int L>
-__device__ __forceinline__ void degree_bwd(const float* __restrict__ src, float* __restrict__ g, int C,
-                                           const float2* __restrict__ tg, float& ga, float& gb, float& gc) {
+template <int L, bool GLOBAL_SRC>
+__device__ __forceinline__ void degree_bwd(const float* src, float* g, int C, const float2* __restrict__ tg,
+                                           float& ga, float& gb, float& gc) {
     float x[2 * L + 1], y[2 * L + 1], w2[2 * L + 1];
-    load_col<L, true>(x, src, C);
-    xrot<L>(x, tg + 2 * WG_LMAX);
+    load_col<L, GLOBAL_SRC>(x, src, C);
+    xrot<L, false>(x, tg + 2 * WG_LMAX);
     jmul<L>(x, w2);
 #pragma unroll
     for (int i = 0; i < 2 * L + 1; ++i) y[i] = w2[i];
-    xrot<L>(y, tg + WG_LMAX);
-    jmul<L>(y, x);                       // x = w4
-    load_col<L, false>(y, g, C);         // y = g
-    xrot_t<L>(y, tg);                    // h4
+    xrot<L, false>(y, tg + WG_LMAX);
+    jmul<L>(y, x);                            // x = w4
+    load_col<L, false>(y, g, C);              // y = g
+    xrot<L, true>(y, tg);                     // h4
     ga += gdot<L>(y, x);
-    jmul<L>(y, x);                       // x = h3
-    xrot_t<L>(x, tg + WG_LMAX);          // h2
+    jmul<L>(y, x);                            // x = h3
+    xrot<L, true>(x, tg + WG_LMAX);           // h2
     gb += gdot<L>(x, w2);
-    jmul<L>(x, y);                       // y = h1
-    xrot_t<L>(y, tg + 2 * WG_LMAX);      // g_s
-    load_col<L, true>(x, src, C);
+    jmul<L>(x, y);                            // y = h1
+    xrot<L, true>(y, tg + 2 * WG_LMAX);       // g_s
+    load_col<L, GLOBAL_SRC>(x, src, C);
     gc += gdot<L>(y, x);
 #pragma unroll
     for (int i = 0; i < 2 * L + 1; ++i) g[i * C] = y[i];
@@ -151,11 +153,13 @@ __host__ __device__ inline int align4i(int x) { return (x + 3) & ~3; }
 
 // ------------------------------------------------------------------ forward
 // SHARED: spectrum is (M,C), the same for every sample (stride-0 expand in the reference).
-template <bool SHARED>
+// CT: compile-time channel count (0 = use the run-time argument).
+template <bool SHARED, int CT>
 __global__ void __launch_bounds__(WG_MAX_THREADS)
 wigner_fwd_kernel(const float* __restrict__ angles, const float* __restrict__ spectrum, float* __restrict__ out,
-                  int64_t N, int lmin, int lmax, int C, int S, int transpose) {
+                  int64_t N, int lmin, int lmax, int Crt, int S, int transpose) {
     extern __shared__ __align__(16) float smem[];
+    const int C = CT > 0 ? CT : Crt;
     const int M = (lmax + 1) * (lmax + 1) - lmin * lmin;
     const int MC = M * C;
     float* tile = smem;
@@ -164,12 +168,15 @@ wigner_fwd_kernel(const float* __restrict__ angles, const float* __restrict__ sp
     const int rows = int(min(int64_t(S), N - n0));
     stage_trig(s_trig, angles, n0, rows, transpose);
     if (!SHARED) tile_g2s(tile, spectrum + n0 * MC, rows * MC);
+    tile_async_wait();
     __syncthreads();
     const int t = threadIdx.x;
     const int s = t / C, c = t - s * C;
     if (s < rows) {
         const float2* tg = reinterpret_cast<const float2*>(s_trig + s * WG_TRIG_STRIDE);
         float* trow = tile + s * MC + c;
+        // shared spectrum: 3 KB read by every thread of every CTA -> stays L1-resident (the kernel streams
+        // nothing else through L1: outputs leave through smem), so it is read in place with LDG.
         const float* srow = SHARED ? spectrum + c : trow;
         int off = 0;
         for (int l = lmin; l <= lmax; ++l) {
@@ -183,36 +190,39 @@ wigner_fwd_kernel(const float* __restrict__ angles, const float* __restrict__ sp
 
 // ------------------------------------------------------------------ backward
 // Persistent CTAs over sample tiles.  workspace (SHARED only): [gridDim.x][MC] partial sums.
-template <bool SHARED>
+template <bool SHARED, int CT>
 __global__ void __launch_bounds__(WG_MAX_THREADS)
 wigner_bwd_kernel(const float* __restrict__ angles, const float* __restrict__ spectrum, const float* __restrict__ gout,
                   float* __restrict__ gangles, float* __restrict__ gspectrum, float* __restrict__ partial,
-                  int64_t N, int lmin, int lmax, int C, int S, int transpose, int64_t ntiles) {
+                  int64_t N, int lmin, int lmax, int Crt, int S, int transpose, int64_t ntiles) {
     extern __shared__ __align__(16) float smem[];
+    const int C = CT > 0 ? CT : Crt;
     const int M = (lmax + 1) * (lmax + 1) - lmin * lmin;
     const int MC = M * C;
     float* tile = smem;
     float* s_trig = tile + align4i(S * MC);
     float* s_gp = s_trig + S * WG_TRIG_STRIDE;          // [S*C][3] per-thread angle-gradient parts
-    float* s_acc = s_gp + align4i(S * C * 3);           // [MC] (SHARED)
+    float* s_acc = s_gp + align4i(S * C * 3);           // [MC] (SHARED) batch-sum of the spectrum gradient
+    float* s_item = s_acc + align4i(MC);                // [MC] (SHARED) the spectrum itself
     const int t = threadIdx.x;
     const int s = t / C, c = t - s * C;
     if (SHARED)
-        for (int o = t; o < MC; o += blockDim.x) s_acc[o] = 0.f;
+        for (int o = t; o < MC; o += blockDim.x) { s_acc[o] = 0.f; s_item[o] = __ldg(spectrum + o); }
     for (int64_t tile_idx = blockIdx.x; tile_idx < ntiles; tile_idx += gridDim.x) {
         const int64_t n0 = tile_idx * S;
         const int rows = int(min(int64_t(S), N - n0));
         stage_trig(s_trig, angles, n0, rows, transpose);
         tile_g2s(tile, gout + n0 * MC, rows * MC);
+        tile_async_wait();
         __syncthreads();
         if (s < rows) {
             const float2* tg = reinterpret_cast<const float2*>(s_trig + s * WG_TRIG_STRIDE);
             float* trow = tile + s * MC + c;
-            const float* srow = SHARED ? spectrum + c : spectrum + (n0 + s) * MC + c;
+            const float* srow = SHARED ? s_item + c : spectrum + (n0 + s) * MC + c;
             float ga = 0.f, gb = 0.f, gc = 0.f;
             int off = 0;
             for (int l = lmin; l <= lmax; ++l) {
-                WG_SWITCH(l, (degree_bwd<L>(srow + off, trow + off, C, tg, ga, gb, gc)));
+                WG_SWITCH(l, (degree_bwd<L, !SHARED>(srow + off, trow + off, C, tg, ga, gb, gc)));
                 off += (2 * l + 1) * C;
             }
             // effective angles (a',b',c') = transpose ? (-c,-b,-a) : (a,b,c)
@@ -223,9 +233,11 @@ wigner_bwd_kernel(const float* __restrict__ angles, const float* __restrict__ sp
         __syncthreads();
         if (SHARED) {
             for (int o = t; o < MC; o += blockDim.x) {
-                float a = 0.f;
-                for (int r = 0; r < rows; ++r) a += tile[r * MC + o];
-                s_acc[o] += a;
+                float a0 = 0.f, a1 = 0.f;
+                int r = 0;
+                for (; r + 1 < rows; r += 2) { a0 += tile[r * MC + o]; a1 += tile[(r + 1) * MC + o]; }
+                if (r < rows) a0 += tile[r * MC + o];
+                s_acc[o] += a0 + a1;
             }
         } else {
             tile_s2g(gspectrum + n0 * MC, tile, rows * MC);
@@ -295,7 +307,7 @@ static int wigner_geometry(const char* name, int64_t N, int lmin, int lmax, int 
     g.S = S;
     g.threads = ((S * C + 31) / 32) * 32;
     g.smem_fwd = size_t(align4i(S * g.MC) + S * WG_TRIG_STRIDE) * 4;
-    g.smem_bwd = size_t(align4i(S * g.MC) + S * WG_TRIG_STRIDE + align4i(S * C * 3) + (shared ? g.MC : 0)) * 4;
+    g.smem_bwd = size_t(align4i(S * g.MC) + S * WG_TRIG_STRIDE + align4i(S * C * 3) + (shared ? 2 * align4i(g.MC) : 0)) * 4;
     if (g.smem_bwd > size_t(di.smem_optin)) { set_error("%s: spectrum row of %d floats does not fit shared memory", name, g.MC); return LV_ERR_UNSUPPORTED; }
     g.ntiles = (N + S - 1) / S;
     if (g.ntiles > 0x7fffffffLL) { set_error("%s: too many samples", name); return LV_ERR_ARG; }
@@ -313,7 +325,30 @@ static int opt_in_smem(K kernel, size_t bytes) {
     return LV_OK;
 }
 
+template <bool SHARED, int CT>
+static int launch_fwd(const WgGeom& g, const float* angles, const float* spectrum, float* out, int64_t N, int lmin,
+                      int lmax, int C, int transpose, cudaStream_t st) {
+    int rc = opt_in_smem(wigner_fwd_kernel<SHARED, CT>, g.smem_fwd);
+    if (rc) return rc;
+    wigner_fwd_kernel<SHARED, CT><<<unsigned(g.ntiles), g.threads, g.smem_fwd, st>>>(angles, spectrum, out, N, lmin, lmax, C, g.S, transpose);
+    return check_launch("wigner_apply_fwd");
+}
+
+template <bool SHARED, int CT>
+static int launch_bwd(const WgGeom& g, const float* angles, const float* spectrum, const float* gout, float* gangles,
+                      float* gspectrum, float* workspace, int64_t N, int lmin, int lmax, int C, int transpose,
+                      cudaStream_t st) {
+    int rc = opt_in_smem(wigner_bwd_kernel<SHARED, CT>, g.smem_bwd);
+    if (rc) return rc;
+    wigner_bwd_kernel<SHARED, CT><<<g.grid_bwd, g.threads, g.smem_bwd, st>>>(angles, spectrum, gout, gangles, SHARED ? nullptr : gspectrum,
+                                                                             SHARED ? workspace : nullptr, N, lmin, lmax, C, g.S, transpose, g.ntiles);
+    return check_launch("wigner_apply_bwd");
+}
+
 }  // namespace lv
+
+// channel counts with a compile-time specialisation: 10 = ActionNet default (decoders.py:11, main.py:168)
+#define WG_DISPATCH_C(C, SHARED, FN, ...) ((C) == 10 ? FN<SHARED, 10>(__VA_ARGS__) : FN<SHARED, 0>(__VA_ARGS__))
 
 // ====================================================================== C ABI
 extern "C" int64_t lv_wigner_bwd_workspace_floats(int64_t N, int lmin, int lmax, int C) {
@@ -330,14 +365,8 @@ extern "C" int lv_wigner_apply_fwd_f32(const float* angles, const float* spectru
     if (N == 0) return LV_OK;
     if (!angles || !spectrum || !out) { lv::set_error("wigner_apply_fwd: null pointer"); return LV_ERR_ARG; }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (shared_spectrum) {
-        if ((rc = lv::opt_in_smem(lv::wigner_fwd_kernel<true>, g.smem_fwd))) return rc;
-        lv::wigner_fwd_kernel<true><<<unsigned(g.ntiles), g.threads, g.smem_fwd, st>>>(angles, spectrum, out, N, lmin, lmax, C, g.S, transpose);
-    } else {
-        if ((rc = lv::opt_in_smem(lv::wigner_fwd_kernel<false>, g.smem_fwd))) return rc;
-        lv::wigner_fwd_kernel<false><<<unsigned(g.ntiles), g.threads, g.smem_fwd, st>>>(angles, spectrum, out, N, lmin, lmax, C, g.S, transpose);
-    }
-    return lv::check_launch("wigner_apply_fwd");
+    if (shared_spectrum) return WG_DISPATCH_C(C, true, lv::launch_fwd, g, angles, spectrum, out, N, lmin, lmax, C, transpose, st);
+    return WG_DISPATCH_C(C, false, lv::launch_fwd, g, angles, spectrum, out, N, lmin, lmax, C, transpose, st);
 }
 
 extern "C" int lv_wigner_apply_bwd_f32(const float* angles, const float* spectrum, const float* gout, float* gangles,
@@ -359,13 +388,10 @@ extern "C" int lv_wigner_apply_bwd_f32(const float* angles, const float* spectru
     if (shared_spectrum) {
         const int64_t need = int64_t(g.grid_bwd) * g.MC;
         if (!workspace || workspace_floats < need) { lv::set_error("wigner_apply_bwd: workspace of %lld floats required", (long long)need); return LV_ERR_ARG; }
-        if ((rc = lv::opt_in_smem(lv::wigner_bwd_kernel<true>, g.smem_bwd))) return rc;
-        lv::wigner_bwd_kernel<true><<<g.grid_bwd, g.threads, g.smem_bwd, st>>>(angles, spectrum, gout, gangles, nullptr, workspace, N, lmin, lmax, C, g.S, transpose, g.ntiles);
-        if ((rc = lv::check_launch("wigner_apply_bwd"))) return rc;
+        rc = WG_DISPATCH_C(C, true, lv::launch_bwd, g, angles, spectrum, gout, gangles, gspectrum, workspace, N, lmin, lmax, C, transpose, st);
+        if (rc) return rc;
         lv::wigner_reduce_partials<<<(g.MC + 31) / 32, dim3(32, 8), 0, st>>>(workspace, gspectrum, g.grid_bwd, g.MC);
         return lv::check_launch("wigner_reduce_partials");
     }
-    if ((rc = lv::opt_in_smem(lv::wigner_bwd_kernel<false>, g.smem_bwd))) return rc;
-    lv::wigner_bwd_kernel<false><<<g.grid_bwd, g.threads, g.smem_bwd, st>>>(angles, spectrum, gout, gangles, gspectrum, nullptr, N, lmin, lmax, C, g.S, transpose, g.ntiles);
-    return lv::check_launch("wigner_apply_bwd");
+    return WG_DISPATCH_C(C, false, lv::launch_bwd, g, angles, spectrum, gout, gangles, gspectrum, workspace, N, lmin, lmax, C, transpose, st);
 }

@@ -38,20 +38,30 @@ def algorithmic_bytes(L, C):
 
 
 class FusedSO3ActionStep:
-    """Buffers + launches for micro-batches of at most ``max_batch`` samples (n = 1 sample per datapoint)."""
+    """Buffers + launches for a shard of ``shard`` samples (n = 1 sample per datapoint), decoded in
+    micro-batches of ``micro`` samples.
 
-    def __init__(self, max_batch, degrees=8, rep_copies=10, k=3, transpose=False, device="cuda"):
-        self.Bm, self.L, self.C, self.k, self.transpose = int(max_batch), int(degrees), int(rep_copies), int(k), bool(transpose)
+    The latent kernels (reparameterize, Euler; ~0.5 kB/sample) run once over the whole shard; only the
+    Wigner action, whose output is 3.2 kB/sample, is micro-batched so that y / g_y never need to be
+    resident for the full shard.
+    """
+
+    LAUNCHES_PER_MICROBATCH = 3      # wigner fwd, wigner bwd, wigner_reduce_partials
+    LAUNCHES_PER_SHARD = 4           # reparam fwd, eazyz fwd, eazyz bwd, reparam bwd
+
+    def __init__(self, shard, micro, degrees=8, rep_copies=10, k=3, transpose=False, device="cuda"):
+        self.shard, self.micro = int(shard), int(micro)
+        self.L, self.C, self.k, self.transpose = int(degrees), int(rep_copies), int(k), bool(transpose)
         self.M = (self.L + 1) ** 2
         self.device = torch.device(device)
         f32 = dict(dtype=torch.float32, device=self.device)
-        self.z = torch.empty((self.Bm, 3, 3), **f32)
-        self.angles = torch.empty((self.Bm, 3), **f32)
-        self.g_angles = torch.empty((self.Bm, 3), **f32)
-        self.g_z = torch.empty((self.Bm, 3, 3), **f32)
-        self.g_item = torch.empty((self.M, self.C), **f32)
+        self.z = torch.empty((self.shard, 3, 3), **f32)
+        self.angles = torch.empty((self.shard, 3), **f32)
+        self.g_angles = torch.empty((self.shard, 3), **f32)
+        self.g_z = torch.empty((self.shard, 3, 3), **f32)
+        self.g_item = torch.empty((self.M, self.C), **f32)      # gradient of the last decoded micro-batch
         with torch.cuda.device(self.device):
-            nws = _cabi.lib().lv_wigner_bwd_workspace_floats(self.Bm, 0, self.L, self.C)
+            nws = _cabi.lib().lv_wigner_bwd_workspace_floats(self.micro, 0, self.L, self.C)
         if nws < 0:
             raise RuntimeError(_cabi.last_error())
         self.nws = nws
@@ -71,23 +81,25 @@ class FusedSO3ActionStep:
         b.record()
         self.events[name].append((a, b))
 
-    def forward(self, mu, sigma, eps, item_rep, y, log_q):
-        """mu (B,3,3), sigma (B,3), eps (B,3) -> y (B,M,C), log_q (B); z / angles stay in the step's buffers."""
-        B = mu.shape[0]
-        st = _stream()
-        p = _cabi.ptr
+    def latent_forward(self, mu, sigma, eps, log_q):
+        """mu (B,3,3), sigma (B,3), eps (B,3) -> log_q (B); z and the Euler angles stay in the step's buffers."""
+        B, st, p = mu.shape[0], _stream(), _cabi.ptr
         self._timed("reparam_fwd", lambda: _cabi.call("lv_so3_reparam_fwd_f32", p(mu), p(sigma), p(eps), p(self.z), p(log_q), 1, B, self.k, st))
         self._timed("eazyz_fwd", lambda: _cabi.call("lv_mat_to_eazyz_fwd_f32", p(self.z), p(self.angles), B, st))
-        self._timed("wigner_fwd", lambda: _cabi.call("lv_wigner_apply_fwd_f32", p(self.angles), p(item_rep), p(y), B, 0, self.L, self.C, 1, int(self.transpose), st))
 
-    def backward(self, mu, sigma, eps, item_rep, g_y, g_log_q, g_mu, g_sigma):
-        """Consumes the z / angles of the preceding forward.  Writes g_mu (B,3,3), g_sigma (B,3), self.g_item (M,C)."""
-        B = mu.shape[0]
-        st = _stream()
-        p = _cabi.ptr
-        self._timed("wigner_bwd", lambda: _cabi.call("lv_wigner_apply_bwd_f32", p(self.angles), p(item_rep), p(g_y), p(self.g_angles), p(self.g_item),
-                                                    p(self.workspace), self.nws, B, 0, self.L, self.C, 1, int(self.transpose), st))
+    def decode_forward(self, lo, hi, item_rep, y):
+        """Wigner action of samples [lo, hi) on item_rep (M,C) -> y (hi-lo, M, C)."""
+        st, p = _stream(), _cabi.ptr
+        self._timed("wigner_fwd", lambda: _cabi.call("lv_wigner_apply_fwd_f32", p(self.angles[lo:hi]), p(item_rep), p(y), hi - lo, 0, self.L, self.C, 1, int(self.transpose), st))
+
+    def decode_backward(self, lo, hi, item_rep, g_y):
+        """g_y (hi-lo, M, C) -> g_angles[lo:hi] and self.g_item (M,C) for this micro-batch."""
+        st, p = _stream(), _cabi.ptr
+        self._timed("wigner_bwd", lambda: _cabi.call("lv_wigner_apply_bwd_f32", p(self.angles[lo:hi]), p(item_rep), p(g_y), p(self.g_angles[lo:hi]), p(self.g_item),
+                                                    p(self.workspace), self.nws, hi - lo, 0, self.L, self.C, 1, int(self.transpose), st))
+
+    def latent_backward(self, mu, sigma, eps, g_log_q, g_mu, g_sigma):
+        """g_angles (from decode_backward) and g_log_q (B) -> g_mu (B,3,3), g_sigma (B,3)."""
+        B, st, p = mu.shape[0], _stream(), _cabi.ptr
         self._timed("eazyz_bwd", lambda: _cabi.call("lv_mat_to_eazyz_bwd_f32", p(self.z), p(self.g_angles), p(self.g_z), B, st))
         self._timed("reparam_bwd", lambda: _cabi.call("lv_so3_reparam_bwd_f32", p(mu), p(sigma), p(eps), p(self.g_z), p(g_log_q), p(g_mu), p(g_sigma), 1, B, self.k, st))
-
-    LAUNCHES_PER_MICROBATCH = 7      # six kernels above + wigner_reduce_partials

@@ -198,7 +198,7 @@ def test_action_net_vs_oracle(mods, L, C, N, tr):
     w = torch.randn(N, M * C, dtype=torch.float64)
 
     def run_oracle(dt):
-        a, it = ang.to(dt).requires_grad_(True), item.to(dt).requires_grad_(True)
+        a, it = ang.detach().clone().to(dt).requires_grad_(True), item.detach().clone().to(dt).requires_grad_(True)
         out = O.action_net_forward(a, it, L, tr)
         (out * w.to(dt)).sum().backward()
         return out.detach(), a.grad, it.grad
@@ -236,7 +236,7 @@ def test_wigner_reference_properties(mods):
     r = lt.random_group_matrices(100, device="cuda")
     D1 = lt.wigner_d_matrix(lt.group_matrix_to_eazyz(r), 1)
     P = torch.tensor([[0., 1, 0], [0, 0, 1], [1, 0, 0]], device="cuda")
-    close(D1, P @ r.transpose(1, 2) @ P.t(), 1e-5, 2e-6)
+    close(D1, P @ r.transpose(1, 2) @ P.t(), 1e-5, 1e-5)
 
 
 def test_wigner_full_size_properties(mods):
