@@ -10,11 +10,18 @@
 // ~25% dense with compile-time coefficients (wigner_gen.cuh, one immediate-operand FMA per
 // non-zero).  One thread owns one (sample, channel) column; the degree-l vector (<= 17 floats)
 // lives in registers.  cos/sin(m*angle), m = 1..8, are computed once per sample by three threads
-// (sincosf + angle-addition recurrence) and shared through smem.  The CTA's (S, M, C) output tile
-// is contiguous in global memory: it is assembled in shared memory and moved with 128-bit
-// coalesced accesses.  The channel count is a template parameter for the common cases so that
-// every tile / spectrum access is base + immediate (no per-access integer math); CT = 0 is the
-// run-time-C fallback.
+// (sincosf + angle-addition recurrence) and shared through smem.
+//
+// Data movement (Blackwell): the CTA's (S, M, C) tile is one contiguous span of HBM.
+//   forward : columns are assembled in shared memory and the whole tile leaves with ONE TMA bulk
+//             store (cp.async.bulk.global.shared::cta) issued by one thread -- no per-thread
+//             copy-out loop, the LSU and the issue slots stay with the math;
+//   backward: the upstream-gradient tile lands by cp.async (all pieces in flight at once), the
+//             spectrum gradient overwrites it in place.
+// Specialisations: the channel count (10, the ActionNet default) and the degree range (0..8 and
+// 0..6) are template parameters for the common cases, so the degree loop is fully unrolled and every
+// tile / spectrum access is base + immediate; <CT = 0, LT = -1> is the run-time fallback for
+// any C <= 256 and any 0 <= lmin <= lmax <= 8.
 //
 // Backward (hand-derived; G = d/dphi X(phi) X(phi)^-1 is the pair generator
 // (G w)_i = (l-i) w_{2l-i}):
@@ -22,8 +29,8 @@
 //      g_a = <h4, G w4>,  g_b = <h2, G w2>,  g_c = <g_s, G s>,   w2 = J X(c) s, w4 = J X(b) w2
 // so only w2 and w4 are recomputed from the spectrum; nothing is saved by the forward.
 // For a shared spectrum (ActionNet.item_rep, decoders.py:53) the per-sample g_s are summed over
-// the batch deterministically: rows of the tile -> per-CTA accumulator in smem (persistent CTAs)
-// -> one partial per CTA -> a second tiny kernel.  No atomics anywhere.
+// the batch deterministically: rows of the tile -> per-CTA accumulator in smem (persistent CTAs,
+// exactly one resident wave) -> one partial per CTA -> a second tiny kernel.  No atomics anywhere.
 //
 // transpose=True (lie_tools.py:249-250): D^T = X(-c) J X(-b) J X(-a), i.e. the same kernels on
 // the angles (-c, -b, -a), with the angle gradients mapped back.
@@ -35,6 +42,7 @@ namespace lv {
 constexpr int WG_LMAX = wg::kGenLmax;
 constexpr int WG_TRIG_STRIDE = 52;   // 3 angles x 8 x (cos,sin) = 48 floats, padded: 16B-aligned rows, 4 samples on distinct bank quads
 constexpr int WG_MAX_THREADS = 256;
+constexpr int WG_MAX_CTAS_PER_SM = 8;   // bound used to size the backward workspace
 
 using wg::jmul;
 
@@ -149,25 +157,66 @@ __device__ __forceinline__ void degree_bwd(const float* src, float* g, int C, co
         default: { constexpr int L = 8; CALL; } break; \
     }
 
+// all degrees of one column.  LT >= 0: degrees 0..LT, fully unrolled (offsets l^2*C are constants);
+// LT < 0: run-time range lmin..lmax.
+template <int L, int LT, bool GLOBAL_SRC>
+__device__ __forceinline__ void fwd_unrolled(const float* srow, float* trow, int C, const float2* tg) {
+    degree_fwd<L, GLOBAL_SRC>(srow + L * L * C, trow + L * L * C, C, tg);
+    if constexpr (L < LT) fwd_unrolled<L + 1, LT, GLOBAL_SRC>(srow, trow, C, tg);
+}
+template <int LT, bool GLOBAL_SRC>
+__device__ __forceinline__ void fwd_degrees(const float* srow, float* trow, int C, const float2* tg, int lmin, int lmax) {
+    if constexpr (LT >= 0) {
+        fwd_unrolled<0, LT, GLOBAL_SRC>(srow, trow, C, tg);
+    } else {
+        int off = 0;
+        for (int l = lmin; l <= lmax; ++l) {
+            WG_SWITCH(l, (degree_fwd<L, GLOBAL_SRC>(srow + off, trow + off, C, tg)));
+            off += (2 * l + 1) * C;
+        }
+    }
+}
+template <int L, int LT, bool GLOBAL_SRC>
+__device__ __forceinline__ void bwd_unrolled(const float* srow, float* trow, int C, const float2* tg, float& ga, float& gb, float& gc) {
+    degree_bwd<L, GLOBAL_SRC>(srow + L * L * C, trow + L * L * C, C, tg, ga, gb, gc);
+    if constexpr (L < LT) bwd_unrolled<L + 1, LT, GLOBAL_SRC>(srow, trow, C, tg, ga, gb, gc);
+}
+template <int LT, bool GLOBAL_SRC>
+__device__ __forceinline__ void bwd_degrees(const float* srow, float* trow, int C, const float2* tg, int lmin, int lmax,
+                                            float& ga, float& gb, float& gc) {
+    if constexpr (LT >= 0) {
+        bwd_unrolled<0, LT, GLOBAL_SRC>(srow, trow, C, tg, ga, gb, gc);
+    } else {
+        int off = 0;
+        for (int l = lmin; l <= lmax; ++l) {
+            WG_SWITCH(l, (degree_bwd<L, GLOBAL_SRC>(srow + off, trow + off, C, tg, ga, gb, gc)));
+            off += (2 * l + 1) * C;
+        }
+    }
+}
+
 __host__ __device__ inline int align4i(int x) { return (x + 3) & ~3; }
+
+// launch bounds of the specialised kernels: 16 samples x 10 channels = 160 threads per CTA
+__host__ __device__ constexpr int wg_threads(int CT) { return CT == 10 ? 160 : WG_MAX_THREADS; }
 
 // ------------------------------------------------------------------ forward
 // SHARED: spectrum is (M,C), the same for every sample (stride-0 expand in the reference).
-// CT: compile-time channel count (0 = use the run-time argument).
-template <bool SHARED, int CT>
-__global__ void __launch_bounds__(WG_MAX_THREADS)
+template <bool SHARED, int CT, int LT>
+__global__ void __launch_bounds__(wg_threads(CT), CT == 10 ? 4 : 1)
 wigner_fwd_kernel(const float* __restrict__ angles, const float* __restrict__ spectrum, float* __restrict__ out,
-                  int64_t N, int lmin, int lmax, int Crt, int S, int transpose) {
+                  int64_t N, int lmin_rt, int lmax_rt, int Crt, int S, int transpose) {
     extern __shared__ __align__(16) float smem[];
     const int C = CT > 0 ? CT : Crt;
+    const int lmin = LT >= 0 ? 0 : lmin_rt, lmax = LT >= 0 ? LT : lmax_rt;
     const int M = (lmax + 1) * (lmax + 1) - lmin * lmin;
     const int MC = M * C;
     float* tile = smem;
     float* s_trig = smem + align4i(S * MC);
     const int64_t n0 = int64_t(blockIdx.x) * S;
     const int rows = int(min(int64_t(S), N - n0));
-    stage_trig(s_trig, angles, n0, rows, transpose);
     if (!SHARED) tile_g2s(tile, spectrum + n0 * MC, rows * MC);
+    stage_trig(s_trig, angles, n0, rows, transpose);
     tile_async_wait();
     __syncthreads();
     const int t = threadIdx.x;
@@ -178,25 +227,37 @@ wigner_fwd_kernel(const float* __restrict__ angles, const float* __restrict__ sp
         // shared spectrum: 3 KB read by every thread of every CTA -> stays L1-resident (the kernel streams
         // nothing else through L1: outputs leave through smem), so it is read in place with LDG.
         const float* srow = SHARED ? spectrum + c : trow;
-        int off = 0;
-        for (int l = lmin; l <= lmax; ++l) {
-            WG_SWITCH(l, (degree_fwd<L, SHARED>(srow + off, trow + off, C, tg)));
-            off += (2 * l + 1) * C;
-        }
+        fwd_degrees<LT, SHARED>(srow, trow, C, tg, lmin, lmax);
     }
-    __syncthreads();
-    tile_s2g(out + n0 * MC, tile, rows * MC);
+    float* gdst = out + n0 * MC;
+    const uint32_t bytes = uint32_t(rows) * uint32_t(MC) * 4u;
+    if ((bytes & 15u) == 0 && (reinterpret_cast<uintptr_t>(gdst) & 15u) == 0) {
+        // TMA bulk store: make the generic-proxy smem writes visible to the async proxy, then one thread
+        // hands the whole tile to the copy engine and waits only until the engine has read it.
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         :: "l"(gdst), "r"(uint32_t(__cvta_generic_to_shared(tile))), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+    } else {
+        __syncthreads();
+        tile_s2g(gdst, tile, rows * MC);
+    }
 }
 
 // ------------------------------------------------------------------ backward
 // Persistent CTAs over sample tiles.  workspace (SHARED only): [gridDim.x][MC] partial sums.
-template <bool SHARED, int CT>
-__global__ void __launch_bounds__(WG_MAX_THREADS)
+template <bool SHARED, int CT, int LT>
+__global__ void __launch_bounds__(wg_threads(CT), CT == 10 ? 3 : 1)
 wigner_bwd_kernel(const float* __restrict__ angles, const float* __restrict__ spectrum, const float* __restrict__ gout,
                   float* __restrict__ gangles, float* __restrict__ gspectrum, float* __restrict__ partial,
-                  int64_t N, int lmin, int lmax, int Crt, int S, int transpose, int64_t ntiles) {
+                  int64_t N, int lmin_rt, int lmax_rt, int Crt, int S, int transpose, int64_t ntiles) {
     extern __shared__ __align__(16) float smem[];
     const int C = CT > 0 ? CT : Crt;
+    const int lmin = LT >= 0 ? 0 : lmin_rt, lmax = LT >= 0 ? LT : lmax_rt;
     const int M = (lmax + 1) * (lmax + 1) - lmin * lmin;
     const int MC = M * C;
     float* tile = smem;
@@ -211,8 +272,8 @@ wigner_bwd_kernel(const float* __restrict__ angles, const float* __restrict__ sp
     for (int64_t tile_idx = blockIdx.x; tile_idx < ntiles; tile_idx += gridDim.x) {
         const int64_t n0 = tile_idx * S;
         const int rows = int(min(int64_t(S), N - n0));
+        tile_g2s(tile, gout + n0 * MC, rows * MC);       // asynchronous: in flight while the trig table is built
         stage_trig(s_trig, angles, n0, rows, transpose);
-        tile_g2s(tile, gout + n0 * MC, rows * MC);
         tile_async_wait();
         __syncthreads();
         if (s < rows) {
@@ -220,11 +281,7 @@ wigner_bwd_kernel(const float* __restrict__ angles, const float* __restrict__ sp
             float* trow = tile + s * MC + c;
             const float* srow = SHARED ? s_item + c : spectrum + (n0 + s) * MC + c;
             float ga = 0.f, gb = 0.f, gc = 0.f;
-            int off = 0;
-            for (int l = lmin; l <= lmax; ++l) {
-                WG_SWITCH(l, (degree_bwd<L, !SHARED>(srow + off, trow + off, C, tg, ga, gb, gc)));
-                off += (2 * l + 1) * C;
-            }
+            bwd_degrees<LT, !SHARED>(srow, trow, C, tg, lmin, lmax, ga, gb, gc);
             // effective angles (a',b',c') = transpose ? (-c,-b,-a) : (a,b,c)
             s_gp[t * 3 + 0] = transpose ? -gc : ga;
             s_gp[t * 3 + 1] = transpose ? -gb : gb;
@@ -232,12 +289,30 @@ wigner_bwd_kernel(const float* __restrict__ angles, const float* __restrict__ sp
         }
         __syncthreads();
         if (SHARED) {
-            for (int o = t; o < MC; o += blockDim.x) {
-                float a0 = 0.f, a1 = 0.f;
-                int r = 0;
-                for (; r + 1 < rows; r += 2) { a0 += tile[r * MC + o]; a1 += tile[(r + 1) * MC + o]; }
-                if (r < rows) a0 += tile[r * MC + o];
-                s_acc[o] += a0 + a1;
+            if ((MC & 1) == 0) {
+                // column sums over the tile rows, four columns per thread with 64-bit LDS (rows are 8B-aligned)
+                const int nq = (MC + 3) >> 2;
+                for (int q = t; q < nq; q += blockDim.x) {
+                    const int o = 4 * q;
+                    const bool full = o + 3 < MC;          // MC even: the tail quad holds exactly two columns
+                    float2 a = make_float2(0.f, 0.f), b = make_float2(0.f, 0.f);
+                    for (int r = 0; r < rows; ++r) {
+                        const float2 u = *reinterpret_cast<const float2*>(tile + r * MC + o);
+                        a.x += u.x; a.y += u.y;
+                        if (full) {
+                            const float2 v = *reinterpret_cast<const float2*>(tile + r * MC + o + 2);
+                            b.x += v.x; b.y += v.y;
+                        }
+                    }
+                    s_acc[o] += a.x; s_acc[o + 1] += a.y;
+                    if (full) { s_acc[o + 2] += b.x; s_acc[o + 3] += b.y; }
+                }
+            } else {
+                for (int o = t; o < MC; o += blockDim.x) {
+                    float a0 = 0.f;
+                    for (int r = 0; r < rows; ++r) a0 += tile[r * MC + o];
+                    s_acc[o] += a0;
+                }
             }
         } else {
             tile_s2g(gspectrum + n0 * MC, tile, rows * MC);
@@ -287,18 +362,19 @@ static DevInfo dev_info() {
     return cache[dev];
 }
 
-struct WgGeom { int M, MC, S, threads; size_t smem_fwd, smem_bwd; int64_t ntiles; int grid_bwd; };
+struct WgGeom { int M, MC, S, threads, sms; size_t smem_fwd, smem_bwd; int64_t ntiles; };
 
-// S = samples per CTA: about 192 threads, tile <= ~52 KB so that four CTAs share an SM.
+// S = samples per CTA: about 192 threads (160 for C = 10), tile <= ~52 KB so that several CTAs share an SM.
 static int wigner_geometry(const char* name, int64_t N, int lmin, int lmax, int C, bool shared, WgGeom& g) {
     if (N < 0 || C <= 0 || lmin < 0 || lmax < lmin) { set_error("%s: bad sizes (N=%lld, C=%d, degrees %d..%d)", name, (long long)N, C, lmin, lmax); return LV_ERR_ARG; }
     if (lmax > WG_LMAX) { set_error("%s: degree %d > %d is not supported by the unrolled kernels", name, lmax, WG_LMAX); return LV_ERR_UNSUPPORTED; }
     if (C > WG_MAX_THREADS) { set_error("%s: more than %d channels unsupported", name, WG_MAX_THREADS); return LV_ERR_UNSUPPORTED; }
     DevInfo di = dev_info();
     if (!di.ok) { set_error("%s: cannot query the CUDA device", name); return int(cudaErrorInvalidDevice); }
+    g.sms = di.sms;
     g.M = (lmax + 1) * (lmax + 1) - lmin * lmin;
     g.MC = g.M * C;
-    int S = 192 / C;
+    int S = (C == 10 ? wg_threads(10) : 192) / C;    // the C = 10 specialisations are bounded to 160 threads
     if (S < 1) S = 1;
     const int by_smem = (52 * 1024) / (g.MC * 4);
     if (S > by_smem) S = by_smem;
@@ -311,9 +387,6 @@ static int wigner_geometry(const char* name, int64_t N, int lmin, int lmax, int 
     if (g.smem_bwd > size_t(di.smem_optin)) { set_error("%s: spectrum row of %d floats does not fit shared memory", name, g.MC); return LV_ERR_UNSUPPORTED; }
     g.ntiles = (N + S - 1) / S;
     if (g.ntiles > 0x7fffffffLL) { set_error("%s: too many samples", name); return LV_ERR_ARG; }
-    const int64_t cap = int64_t(di.sms) * 4;
-    g.grid_bwd = int(g.ntiles < cap ? g.ntiles : cap);
-    if (g.grid_bwd < 1) g.grid_bwd = 1;
     return LV_OK;
 }
 
@@ -325,36 +398,53 @@ static int opt_in_smem(K kernel, size_t bytes) {
     return LV_OK;
 }
 
-template <bool SHARED, int CT>
+template <bool SHARED, int CT, int LT>
 static int launch_fwd(const WgGeom& g, const float* angles, const float* spectrum, float* out, int64_t N, int lmin,
                       int lmax, int C, int transpose, cudaStream_t st) {
-    int rc = opt_in_smem(wigner_fwd_kernel<SHARED, CT>, g.smem_fwd);
+    int rc = opt_in_smem(wigner_fwd_kernel<SHARED, CT, LT>, g.smem_fwd);
     if (rc) return rc;
-    wigner_fwd_kernel<SHARED, CT><<<unsigned(g.ntiles), g.threads, g.smem_fwd, st>>>(angles, spectrum, out, N, lmin, lmax, C, g.S, transpose);
+    wigner_fwd_kernel<SHARED, CT, LT><<<unsigned(g.ntiles), g.threads, g.smem_fwd, st>>>(angles, spectrum, out, N, lmin, lmax, C, g.S, transpose);
     return check_launch("wigner_apply_fwd");
 }
 
-template <bool SHARED, int CT>
+// persistent grid = exactly the CTAs that are resident at once (a second partial wave would run alone)
+template <bool SHARED, int CT, int LT>
 static int launch_bwd(const WgGeom& g, const float* angles, const float* spectrum, const float* gout, float* gangles,
-                      float* gspectrum, float* workspace, int64_t N, int lmin, int lmax, int C, int transpose,
-                      cudaStream_t st) {
-    int rc = opt_in_smem(wigner_bwd_kernel<SHARED, CT>, g.smem_bwd);
+                      float* gspectrum, float* workspace, int64_t workspace_floats, int64_t N, int lmin, int lmax, int C,
+                      int transpose, cudaStream_t st, int* grid_out) {
+    int rc = opt_in_smem(wigner_bwd_kernel<SHARED, CT, LT>, g.smem_bwd);
     if (rc) return rc;
-    wigner_bwd_kernel<SHARED, CT><<<g.grid_bwd, g.threads, g.smem_bwd, st>>>(angles, spectrum, gout, gangles, SHARED ? nullptr : gspectrum,
-                                                                             SHARED ? workspace : nullptr, N, lmin, lmax, C, g.S, transpose, g.ntiles);
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wigner_bwd_kernel<SHARED, CT, LT>, g.threads, g.smem_bwd);
+    if (e != cudaSuccess || per_sm < 1) { set_error("wigner_apply_bwd: occupancy query failed (%s)", cudaGetErrorString(e)); return e != cudaSuccess ? int(e) : LV_ERR_UNSUPPORTED; }
+    if (per_sm > WG_MAX_CTAS_PER_SM) per_sm = WG_MAX_CTAS_PER_SM;
+    const int64_t cap = int64_t(g.sms) * per_sm;
+    const int grid = int(g.ntiles < cap ? g.ntiles : cap);
+    if (SHARED && (!workspace || workspace_floats < int64_t(grid) * g.MC)) {
+        set_error("wigner_apply_bwd: workspace of %lld floats required", (long long)(int64_t(grid) * g.MC));
+        return LV_ERR_ARG;
+    }
+    *grid_out = grid;
+    wigner_bwd_kernel<SHARED, CT, LT><<<grid, g.threads, g.smem_bwd, st>>>(angles, spectrum, gout, gangles, SHARED ? nullptr : gspectrum,
+                                                                           SHARED ? workspace : nullptr, N, lmin, lmax, C, g.S, transpose, g.ntiles);
     return check_launch("wigner_apply_bwd");
 }
 
 }  // namespace lv
 
-// channel counts with a compile-time specialisation: 10 = ActionNet default (decoders.py:11, main.py:168)
-#define WG_DISPATCH_C(C, SHARED, FN, ...) ((C) == 10 ? FN<SHARED, 10>(__VA_ARGS__) : FN<SHARED, 0>(__VA_ARGS__))
+// compile-time specialisations: 10 channels (ActionNet default, decoders.py:11 / main.py:168) with degrees
+// 0..8 (BASELINE configs 3, 5) or 0..6 (config 4); everything else takes the run-time instantiation.
+#define WG_DISPATCH(C, lmin, lmax, SHARED, FN, ...)                              \
+    ((C) == 10 && (lmin) == 0 && (lmax) == 8 ? FN<SHARED, 10, 8>(__VA_ARGS__)    \
+     : (C) == 10 && (lmin) == 0 && (lmax) == 6 ? FN<SHARED, 10, 6>(__VA_ARGS__)  \
+                                               : FN<SHARED, 0, -1>(__VA_ARGS__))
 
 // ====================================================================== C ABI
 extern "C" int64_t lv_wigner_bwd_workspace_floats(int64_t N, int lmin, int lmax, int C) {
     lv::WgGeom g;
     if (lv::wigner_geometry("wigner_bwd_workspace", N, lmin, lmax, C, true, g) != LV_OK) return -1;
-    return int64_t(g.grid_bwd) * g.MC;
+    const int64_t cap = int64_t(g.sms) * lv::WG_MAX_CTAS_PER_SM;
+    return (g.ntiles < cap ? g.ntiles : cap) * g.MC;
 }
 
 extern "C" int lv_wigner_apply_fwd_f32(const float* angles, const float* spectrum, float* out, int64_t N, int lmin,
@@ -365,8 +455,8 @@ extern "C" int lv_wigner_apply_fwd_f32(const float* angles, const float* spectru
     if (N == 0) return LV_OK;
     if (!angles || !spectrum || !out) { lv::set_error("wigner_apply_fwd: null pointer"); return LV_ERR_ARG; }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (shared_spectrum) return WG_DISPATCH_C(C, true, lv::launch_fwd, g, angles, spectrum, out, N, lmin, lmax, C, transpose, st);
-    return WG_DISPATCH_C(C, false, lv::launch_fwd, g, angles, spectrum, out, N, lmin, lmax, C, transpose, st);
+    if (shared_spectrum) return WG_DISPATCH(C, lmin, lmax, true, lv::launch_fwd, g, angles, spectrum, out, N, lmin, lmax, C, transpose, st);
+    return WG_DISPATCH(C, lmin, lmax, false, lv::launch_fwd, g, angles, spectrum, out, N, lmin, lmax, C, transpose, st);
 }
 
 extern "C" int lv_wigner_apply_bwd_f32(const float* angles, const float* spectrum, const float* gout, float* gangles,
@@ -385,13 +475,12 @@ extern "C" int lv_wigner_apply_bwd_f32(const float* angles, const float* spectru
         return LV_OK;
     }
     if (!angles || !spectrum || !gout || !gangles) { lv::set_error("wigner_apply_bwd: null pointer"); return LV_ERR_ARG; }
+    int grid = 0;
     if (shared_spectrum) {
-        const int64_t need = int64_t(g.grid_bwd) * g.MC;
-        if (!workspace || workspace_floats < need) { lv::set_error("wigner_apply_bwd: workspace of %lld floats required", (long long)need); return LV_ERR_ARG; }
-        rc = WG_DISPATCH_C(C, true, lv::launch_bwd, g, angles, spectrum, gout, gangles, gspectrum, workspace, N, lmin, lmax, C, transpose, st);
+        rc = WG_DISPATCH(C, lmin, lmax, true, lv::launch_bwd, g, angles, spectrum, gout, gangles, gspectrum, workspace, workspace_floats, N, lmin, lmax, C, transpose, st, &grid);
         if (rc) return rc;
-        lv::wigner_reduce_partials<<<(g.MC + 31) / 32, dim3(32, 8), 0, st>>>(workspace, gspectrum, g.grid_bwd, g.MC);
+        lv::wigner_reduce_partials<<<(g.MC + 31) / 32, dim3(32, 8), 0, st>>>(workspace, gspectrum, grid, g.MC);
         return lv::check_launch("wigner_reduce_partials");
     }
-    return WG_DISPATCH_C(C, false, lv::launch_bwd, g, angles, spectrum, gout, gangles, gspectrum, workspace, N, lmin, lmax, C, transpose, st);
+    return WG_DISPATCH(C, lmin, lmax, false, lv::launch_bwd, g, angles, spectrum, gout, gangles, gspectrum, workspace, workspace_floats, N, lmin, lmax, C, transpose, st, &grid);
 }
