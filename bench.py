@@ -253,6 +253,18 @@ def run_ours(args):
     out_h = torch.empty(1 + M * CHANNELS).pin_memory()
     item_p = item.clone().requires_grad_(True)
 
+    class DotLoss(torch.autograd.Function):
+        """sum(y * g) whose backward hands g itself upstream (the stand-in decoder's gradient) instead of
+        materialising a fresh (micro, 810) product tensor."""
+        @staticmethod
+        def forward(ctx, yv, g):
+            ctx.g = g
+            return torch.dot(yv.reshape(-1), g.reshape(-1))
+
+        @staticmethod
+        def backward(ctx, go):
+            return ctx.g, None      # d loss / d y = g (upstream gradient of the scalar loss is 1)
+
     def e2e_step():
         item_p.grad = None
         loss_acc = torch.zeros((), device=dev)
@@ -280,7 +292,7 @@ def run_ours(args):
             z, lq = rp.so3_reparameterize(m, s, stage[b][2], K_WIND)
             ang = lt.group_matrix_to_eazyz(z[0])
             yy = _ops.WignerApply.apply(ang, item_p, 0, L_MAX, False)
-            loss = (yy.view(micro, -1) * gy[i % NBUF]).sum() + torch.dot(lq[0], glq[i * micro:(i + 1) * micro])
+            loss = DotLoss.apply(yy.view(micro, -1), gy[i % NBUF]) + torch.dot(lq[0], glq[i * micro:(i + 1) * micro])
             loss.backward()
             loss_acc += loss.detach()
             stage[b][0].grad = None

@@ -44,6 +44,36 @@ if __name__ == "__main__":
     ref = lt.block_wigner_matrix_multiply(ang, item.expand(B, -1, -1), L).view(B, -1)
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     P = lambda t: ctypes.c_void_p(t.data_ptr())
+    if sys.argv[1] in ("bwdcm", "bwd2cm"):
+        gy = [torch.randn(B, M * C, device=dev) for _ in range(3)]
+        gang = torch.empty(B, 3, device=dev)
+        part = torch.zeros(148 * 8 * M * C, device=dev)
+        import lie_vae_b200._ops as ops
+        a_ref = ang.clone().requires_grad_(True)
+        it_ref = item.clone().requires_grad_(True)
+        (ops.WignerApply.apply(a_ref, it_ref, 0, L, False).view(B, -1) * gy[0]).sum().backward()
+        for gm in [int(v) for v in sys.argv[2].split(",")]:
+            def run(i):
+                fn = lib.exp_wigner_bwdcm if sys.argv[1] == "bwdcm" else lib.exp_wigner_bwd2cm
+                rc = fn(P(ang), P(item), P(gy[i % 3]), P(gang), P(part), ctypes.c_int64(B), 148 * gm, st)
+                assert rc == 0, rc
+            run(0)
+            torch.cuda.synchronize()
+            gi = part[:148 * gm * M * C].view(148 * gm, M, C).sum(0)
+            err_a = float((gang - a_ref.grad).abs().max())
+            err_i = float((gi - it_ref.grad).abs().max() / it_ref.grad.abs().max())
+            for i in range(3):
+                run(i)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(20):
+                run(i)
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / 20
+            print(sys.argv[1] + " grid 148x%d: %.4f ms  %.0f GB/s  err_angles %.2e err_item(rel) %.2e" % (gm, ms, 3264 * B / ms / 1e6, err_a, err_i), flush=True)
+        raise SystemExit(0)
     if sys.argv[1] == "bwd2":
         gy = [torch.randn(B, M * C, device=dev) for _ in range(3)]
         gang = torch.empty(B, 3, device=dev)

@@ -546,3 +546,239 @@ extern "C" int exp_wigner_bwd2(int var, const float* angles, const float* spectr
         default: return -1;
     }
 }
+
+// ===================================================================== channel-major backward
+// warp = one channel, lane = one of 32 samples: trig loads are dense (no 10x broadcast waste), item loads are
+// warp-uniform, tile accesses are 2-way conflicted (row stride 810 words) but serve 32 samples each.
+constexpr int CM_S = 32;
+template <int L, bool TRANSPOSED>
+__device__ __forceinline__ void xrot_cm(float (&x)[2 * L + 1], const float4* __restrict__ cs4) {
+#pragma unroll
+    for (int p = 0; p < (L + 1) / 2; ++p) {
+        float4 t = cs4[p * CM_S];
+        if (TRANSPOSED) { t.y = -t.y; t.w = -t.w; }
+        { const int m = 2 * p + 1; const float a = x[L - m], b = x[L + m]; x[L - m] = fmaf(t.x, a, t.y * b); x[L + m] = fmaf(t.x, b, -(t.y * a)); }
+        if (2 * p + 2 <= L) { const int m = 2 * p + 2; const float a = x[L - m], b = x[L + m]; x[L - m] = fmaf(t.z, a, t.w * b); x[L + m] = fmaf(t.z, b, -(t.w * a)); }
+    }
+}
+template <int L>
+__device__ __forceinline__ void degree_bwd_cm(const float* __restrict__ src, float* g, const float4* tg, float& ga, float& gb, float& gc) {
+    float x[2 * L + 1], y[2 * L + 1], w2[2 * L + 1];
+#pragma unroll
+    for (int i = 0; i < 2 * L + 1; ++i) x[i] = __ldg(src + i * C);
+    xrot_cm<L, false>(x, tg + 8 * CM_S);
+    jmul<L>(x, w2);
+#pragma unroll
+    for (int i = 0; i < 2 * L + 1; ++i) y[i] = w2[i];
+    xrot_cm<L, false>(y, tg + 4 * CM_S);
+    jmul<L>(y, x);
+#pragma unroll
+    for (int i = 0; i < 2 * L + 1; ++i) y[i] = g[i * C];
+    xrot_cm<L, true>(y, tg);
+    ga += gdot<L>(y, x);
+    jmul<L>(y, x);
+    xrot_cm<L, true>(x, tg + 4 * CM_S);
+    gb += gdot<L>(x, w2);
+    jmul<L>(x, y);
+    xrot_cm<L, true>(y, tg + 8 * CM_S);
+#pragma unroll
+    for (int i = 0; i < 2 * L + 1; ++i) x[i] = __ldg(src + i * C);
+    gc += gdot<L>(y, x);
+#pragma unroll
+    for (int i = 0; i < 2 * L + 1; ++i) g[i * C] = y[i];
+}
+template <int L>
+__device__ __forceinline__ void degrees_bwd_cm_from(const float* srow, float* trow, const float4* tg, float& ga, float& gb, float& gc) {
+    degree_bwd_cm<L>(srow + L * L * C, trow + L * L * C, tg, ga, gb, gc);
+    if constexpr (L < LMAX) degrees_bwd_cm_from<L + 1>(srow, trow, tg, ga, gb, gc);
+}
+
+__global__ void __launch_bounds__(320, 2)
+bwdcm_kernel(const float* __restrict__ angles, const float* __restrict__ spectrum, const float* __restrict__ gout,
+             float* __restrict__ gangles, float* __restrict__ partial, int64_t N, int64_t ntiles) {
+    extern __shared__ __align__(16) float smem[];
+    float* tile = smem;                                             // [32][810]
+    float4* s_trig = reinterpret_cast<float4*>(tile + CM_S * MC);    // [3][4][32] float4
+    float* s_gp = reinterpret_cast<float*>(s_trig + 12 * CM_S);      // [10][32][3]
+    const int t = threadIdx.x, c = t >> 5, s = t & 31;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t tile_idx = blockIdx.x; tile_idx < ntiles; tile_idx += gridDim.x) {
+        const int64_t n0 = tile_idx * CM_S;
+        const int rows = int(min(int64_t(CM_S), N - n0));
+        tile_g2s(tile, gout + n0 * MC, rows * MC);
+        if (t < rows * 3) {
+            const int ss = t / 3, a = t - 3 * ss;
+            float s1, c1;
+            sincosf(__ldg(angles + n0 * 3 + t), &s1, &c1);
+            float cm = c1, sm = s1;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                float4 v;
+                v.x = cm; v.y = sm;
+                float cn = fmaf(cm, c1, -(sm * s1)); sm = fmaf(sm, c1, cm * s1); cm = cn;
+                v.z = cm; v.w = sm;
+                cn = fmaf(cm, c1, -(sm * s1)); sm = fmaf(sm, c1, cm * s1); cm = cn;
+                s_trig[(a * 4 + p) * CM_S + ss] = v;
+            }
+        }
+        tile_async_wait();
+        __syncthreads();
+        if (s < rows) {
+            float ga = 0.f, gb = 0.f, gc = 0.f;
+            degrees_bwd_cm_from<0>(spectrum + c, tile + s * MC + c, s_trig + s, ga, gb, gc);
+            s_gp[(c * CM_S + s) * 3 + 0] = ga; s_gp[(c * CM_S + s) * 3 + 1] = gb; s_gp[(c * CM_S + s) * 3 + 2] = gc;
+        }
+        __syncthreads();
+        if (t < 203) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            const bool full = t < 202;
+            for (int r = 0; r < rows; ++r) {
+                const float2 u = *reinterpret_cast<const float2*>(tile + r * MC + 4 * t);
+                a.x += u.x; a.y += u.y;
+                if (full) { const float2 v = *reinterpret_cast<const float2*>(tile + r * MC + 4 * t + 2); a.z += v.x; a.w += v.y; }
+            }
+            acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+        } else if (t >= 224 && t < 224 + rows * 3) {
+            const int j = t - 224, ss = j / 3, a = j - 3 * ss;
+            float sum = 0.f;
+#pragma unroll
+            for (int cc = 0; cc < C; ++cc) sum += s_gp[(cc * CM_S + ss) * 3 + a];
+            gangles[n0 * 3 + j] = sum;
+        }
+        __syncthreads();
+    }
+    float* prow = partial + int64_t(blockIdx.x) * MC;
+    if (t < 203) { prow[4 * t] = acc.x; prow[4 * t + 1] = acc.y; if (t < 202) { prow[4 * t + 2] = acc.z; prow[4 * t + 3] = acc.w; } }
+}
+
+extern "C" int exp_wigner_bwdcm(const float* angles, const float* spectrum, const float* gout, float* gangles, float* partial,
+                                int64_t N, int grid, void* stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t smem = size_t(CM_S * MC) * 4 + 12 * CM_S * 16 + C * CM_S * 3 * 4;
+    cudaError_t e = cudaFuncSetAttribute(bwdcm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return int(e);
+    bwdcm_kernel<<<grid, 320, smem, st>>>(angles, spectrum, gout, gangles, partial, N, (N + CM_S - 1) / CM_S);
+    return int(cudaGetLastError());
+}
+
+// ===================================================================== packed + channel-major backward
+// warp = one channel PAIR (f32x2), lane = sample; CTA = 5 warps x 32 samples.
+template <int L, bool TRANSPOSED>
+__device__ __forceinline__ void xrot2_cm(f32x2_t (&x)[2 * L + 1], const float4* __restrict__ cs4) {
+#pragma unroll
+    for (int p = 0; p < (L + 1) / 2; ++p) {
+        float4 t = cs4[p * CM_S];
+        if (TRANSPOSED) { t.y = -t.y; t.w = -t.w; }
+        { const int m = 2 * p + 1; const f32x2_t a = x[L - m], b = x[L + m]; x[L - m] = vfma(t.x, a, vmul(t.y, b)); x[L + m] = vfma(t.x, b, vmul(-t.y, a)); }
+        if (2 * p + 2 <= L) { const int m = 2 * p + 2; const f32x2_t a = x[L - m], b = x[L + m]; x[L - m] = vfma(t.z, a, vmul(t.w, b)); x[L + m] = vfma(t.z, b, vmul(-t.w, a)); }
+    }
+}
+template <int L>
+__device__ __forceinline__ void degree_bwd2_cm(const f32x2_t* __restrict__ src, f32x2_t* g, const float4* tg, f32x2_t (&acc)[6]) {
+    f32x2_t x[2 * L + 1], y[2 * L + 1], w2[2 * L + 1];
+#pragma unroll
+    for (int i = 0; i < 2 * L + 1; ++i) x[i] = __ldg(src + i * CP);
+    xrot2_cm<L, false>(x, tg + 8 * CM_S);
+    jmul<L>(x, w2);
+#pragma unroll
+    for (int i = 0; i < 2 * L + 1; ++i) y[i] = w2[i];
+    xrot2_cm<L, false>(y, tg + 4 * CM_S);
+    jmul<L>(y, x);
+#pragma unroll
+    for (int i = 0; i < 2 * L + 1; ++i) y[i] = g[i * CP];
+    xrot2_cm<L, true>(y, tg);
+    gdot2<L>(y, x, acc[0], acc[1]);
+    jmul<L>(y, x);
+    xrot2_cm<L, true>(x, tg + 4 * CM_S);
+    gdot2<L>(x, w2, acc[2], acc[3]);
+    jmul<L>(x, y);
+    xrot2_cm<L, true>(y, tg + 8 * CM_S);
+#pragma unroll
+    for (int i = 0; i < 2 * L + 1; ++i) x[i] = __ldg(src + i * CP);
+    gdot2<L>(y, x, acc[4], acc[5]);
+#pragma unroll
+    for (int i = 0; i < 2 * L + 1; ++i) g[i * CP] = y[i];
+}
+template <int L>
+__device__ __forceinline__ void degrees_bwd2_cm_from(const f32x2_t* srow, f32x2_t* trow, const float4* tg, f32x2_t (&acc)[6]) {
+    degree_bwd2_cm<L>(srow + L * L * CP, trow + L * L * CP, tg, acc);
+    if constexpr (L < LMAX) degrees_bwd2_cm_from<L + 1>(srow, trow, tg, acc);
+}
+
+__global__ void __launch_bounds__(160, 2)
+bwd2cm_kernel(const float* __restrict__ angles, const float* __restrict__ spectrum, const float* __restrict__ gout,
+              float* __restrict__ gangles, float* __restrict__ partial, int64_t N, int64_t ntiles) {
+    extern __shared__ __align__(16) float smem[];
+    float* tile = smem;
+    float4* s_trig = reinterpret_cast<float4*>(tile + CM_S * MC);
+    float* s_gp = reinterpret_cast<float*>(s_trig + 12 * CM_S);      // [5][32][3]
+    const int t = threadIdx.x, p = t >> 5, s = t & 31;
+    float4 acc_a = make_float4(0.f, 0.f, 0.f, 0.f), acc_b = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t tile_idx = blockIdx.x; tile_idx < ntiles; tile_idx += gridDim.x) {
+        const int64_t n0 = tile_idx * CM_S;
+        const int rows = int(min(int64_t(CM_S), N - n0));
+        tile_g2s(tile, gout + n0 * MC, rows * MC);
+        if (t < rows * 3) {
+            const int ss = t / 3, a = t - 3 * ss;
+            float s1, c1;
+            sincosf(__ldg(angles + n0 * 3 + t), &s1, &c1);
+            float cm = c1, sm = s1;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float4 v;
+                v.x = cm; v.y = sm;
+                float cn = fmaf(cm, c1, -(sm * s1)); sm = fmaf(sm, c1, cm * s1); cm = cn;
+                v.z = cm; v.w = sm;
+                cn = fmaf(cm, c1, -(sm * s1)); sm = fmaf(sm, c1, cm * s1); cm = cn;
+                s_trig[(a * 4 + q) * CM_S + ss] = v;
+            }
+        }
+        tile_async_wait();
+        __syncthreads();
+        if (s < rows) {
+            f32x2_t acc[6] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
+            degrees_bwd2_cm_from<0>(reinterpret_cast<const f32x2_t*>(spectrum) + p, reinterpret_cast<f32x2_t*>(tile + s * MC) + p, s_trig + s, acc);
+            const float2 a0 = vunpack(acc[0]), a1 = vunpack(acc[1]), b0 = vunpack(acc[2]), b1 = vunpack(acc[3]), c0 = vunpack(acc[4]), c1 = vunpack(acc[5]);
+            s_gp[(p * CM_S + s) * 3 + 0] = (a0.x - a1.x) + (a0.y - a1.y);
+            s_gp[(p * CM_S + s) * 3 + 1] = (b0.x - b1.x) + (b0.y - b1.y);
+            s_gp[(p * CM_S + s) * 3 + 2] = (c0.x - c1.x) + (c0.y - c1.y);
+        }
+        __syncthreads();
+        for (int k = 0; k < 2; ++k) {
+            const int q = t + k * 160;
+            if (q < 203) {
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                const bool full = q < 202;
+                for (int r = 0; r < rows; ++r) {
+                    const float2 u = *reinterpret_cast<const float2*>(tile + r * MC + 4 * q);
+                    a.x += u.x; a.y += u.y;
+                    if (full) { const float2 v = *reinterpret_cast<const float2*>(tile + r * MC + 4 * q + 2); a.z += v.x; a.w += v.y; }
+                }
+                if (k == 0) { acc_a.x += a.x; acc_a.y += a.y; acc_a.z += a.z; acc_a.w += a.w; }
+                else { acc_b.x += a.x; acc_b.y += a.y; acc_b.z += a.z; acc_b.w += a.w; }
+            }
+        }
+        if (t >= 64 && t < 64 + rows * 3) {
+            const int j = t - 64, ss = j / 3, a = j - 3 * ss;
+            float sum = 0.f;
+#pragma unroll
+            for (int cc = 0; cc < CP; ++cc) sum += s_gp[(cc * CM_S + ss) * 3 + a];
+            gangles[n0 * 3 + j] = sum;
+        }
+        __syncthreads();
+    }
+    float* prow = partial + int64_t(blockIdx.x) * MC;
+    if (t < 203) { prow[4 * t] = acc_a.x; prow[4 * t + 1] = acc_a.y; if (t < 202) { prow[4 * t + 2] = acc_a.z; prow[4 * t + 3] = acc_a.w; } }
+    const int q2 = t + 160;
+    if (q2 < 203) { prow[4 * q2] = acc_b.x; prow[4 * q2 + 1] = acc_b.y; if (q2 < 202) { prow[4 * q2 + 2] = acc_b.z; prow[4 * q2 + 3] = acc_b.w; } }
+}
+
+extern "C" int exp_wigner_bwd2cm(const float* angles, const float* spectrum, const float* gout, float* gangles, float* partial,
+                                 int64_t N, int grid, void* stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t smem = size_t(CM_S * MC) * 4 + 12 * CM_S * 16 + CP * CM_S * 3 * 4;
+    cudaError_t e = cudaFuncSetAttribute(bwd2cm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return int(e);
+    bwd2cm_kernel<<<grid, 160, smem, st>>>(angles, spectrum, gout, gangles, partial, N, (N + CM_S - 1) / CM_S);
+    return int(cudaGetLastError());
+}
