@@ -253,18 +253,6 @@ def run_ours(args):
     out_h = torch.empty(1 + M * CHANNELS).pin_memory()
     item_p = item.clone().requires_grad_(True)
 
-    class DotLoss(torch.autograd.Function):
-        """sum(y * g) whose backward hands g itself upstream (the stand-in decoder's gradient) instead of
-        materialising a fresh (micro, 810) product tensor."""
-        @staticmethod
-        def forward(ctx, yv, g):
-            ctx.g = g
-            return torch.dot(yv.reshape(-1), g.reshape(-1))
-
-        @staticmethod
-        def backward(ctx, go):
-            return ctx.g, None      # d loss / d y = g (upstream gradient of the scalar loss is 1)
-
     def e2e_step():
         item_p.grad = None
         loss_acc = torch.zeros((), device=dev)
@@ -292,15 +280,18 @@ def run_ours(args):
             z, lq = rp.so3_reparameterize(m, s, stage[b][2], K_WIND)
             ang = lt.group_matrix_to_eazyz(z[0])
             yy = _ops.WignerApply.apply(ang, item_p, 0, L_MAX, False)
-            loss = DotLoss.apply(yy.view(micro, -1), gy[i % NBUF]) + torch.dot(lq[0], glq[i * micro:(i + 1) * micro])
-            loss.backward()
-            loss_acc += loss.detach()
+            # the decoder that would consume y is outside the hot path: its gradient g_y (and g_log_q) is handed
+            # to autograd directly, exactly as a downstream module's backward would
+            glq_i = glq[i * micro:(i + 1) * micro]
+            torch.autograd.backward([yy, lq], [gy[i % NBUF].view(micro, M, CHANNELS), glq_i.view(1, micro)])
+            loss_acc += torch.dot(lq.detach()[0], glq_i)
             stage[b][0].grad = None
             stage[b][1].grad = None
             stage[b][0].requires_grad_(False)
             stage[b][1].requires_grad_(False)
             freed[b].record(main)
-        red[0] = loss_acc
+        # loss = sum(y * g_y) + sum(log_q * g_lq), with sum(y * g_y) = <item_rep, grad item_rep> (y is linear in item_rep)
+        red[0] = loss_acc + (item_p.detach() * item_p.grad).sum()
         red[1:] = item_p.grad.view(-1)
         if world > 1:
             dist.all_reduce(red)
@@ -351,8 +342,11 @@ def run_ours(args):
                     "h2d_bytes_per_step": n_loc * 60, "d2h_bytes_per_step": 4 * (1 + M * CHANNELS),
                     "api": "so3_reparameterize -> group_matrix_to_eazyz -> WignerApply (autograd), pinned host mu/sigma/eps, double-buffered copies"},
             "gpu_launches": (step_obj.LAUNCHES_PER_MICROBATCH * n_micro + step_obj.LAUNCHES_PER_SHARD) * args.steps,
-            "roofline": {"bound": "hbm", "kernel": "wigner_bwd_kernel<shared>", "achieved": kernels[dom]["gbs"], "peak": peak,
-                         "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "kernel": "wigner_bwd_kernel<shared,10,8>", "achieved": kernels[dom]["gbs"], "peak": peak,
+                         "unit": "GB/s", "frac": kernels[dom]["frac"],
+                         # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture
+                         # profiles/r01_ncu_wigner_v2_summary.txt (852.63 MB + 7.61 MB at 2^18 samples per launch)
+                         "traffic": 860.24e6 * (micro / 262144.0), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": abytes[dom] * micro},
             "pipeline_roofline": {"bytes_per_sample": 6656, "achieved_gbs": round(value / world * 6656 / 1e9, 1),
                                   "frac": round(value / world * 6656 / 1e9 / peak, 4)},

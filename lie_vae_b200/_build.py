@@ -28,7 +28,8 @@ def is_stale():
 
 def _compile_one(args):
     src, obj, verbose = args
-    cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+    extra = os.environ.get("LV_NVCC_EXTRA", "").split()      # build-time experiments only
+    cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f != "-shared"] + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
     proc = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     return src, proc.returncode, proc.stdout + proc.stderr
 

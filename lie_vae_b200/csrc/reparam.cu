@@ -121,7 +121,8 @@ __device__ __forceinline__ void winding_grad(float theta, float a, int krt, floa
 template <int W>
 __device__ __forceinline__ void stage_bcast(float* __restrict__ dst, const float* __restrict__ src,
                                             int64_t i0, int rows, int64_t B) {
-    const int64_t b0 = i0 % B;
+    // n == 1 (the training case): rows are not broadcast and the emulated 64-bit modulo is skipped
+    const int64_t b0 = i0 < B ? i0 : i0 % B;
     if (b0 + rows <= B) {
         tile_g2s(dst, src + b0 * W, rows * W);
     } else {

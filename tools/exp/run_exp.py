@@ -44,7 +44,7 @@ if __name__ == "__main__":
     ref = lt.block_wigner_matrix_multiply(ang, item.expand(B, -1, -1), L).view(B, -1)
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     P = lambda t: ctypes.c_void_p(t.data_ptr())
-    if sys.argv[1] in ("bwdcm", "bwd2cm"):
+    if sys.argv[1] in ("bwdcm", "bwd2cm", "bwdws"):
         gy = [torch.randn(B, M * C, device=dev) for _ in range(3)]
         gang = torch.empty(B, 3, device=dev)
         part = torch.zeros(148 * 8 * M * C, device=dev)
@@ -54,7 +54,7 @@ if __name__ == "__main__":
         (ops.WignerApply.apply(a_ref, it_ref, 0, L, False).view(B, -1) * gy[0]).sum().backward()
         for gm in [int(v) for v in sys.argv[2].split(",")]:
             def run(i):
-                fn = lib.exp_wigner_bwdcm if sys.argv[1] == "bwdcm" else lib.exp_wigner_bwd2cm
+                fn = {"bwdcm": lib.exp_wigner_bwdcm, "bwd2cm": lib.exp_wigner_bwd2cm, "bwdws": lib.exp_wigner_bwdws}[sys.argv[1]]
                 rc = fn(P(ang), P(item), P(gy[i % 3]), P(gang), P(part), ctypes.c_int64(B), 148 * gm, st)
                 assert rc == 0, rc
             run(0)

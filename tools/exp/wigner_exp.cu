@@ -782,3 +782,168 @@ extern "C" int exp_wigner_bwd2cm(const float* angles, const float* spectrum, con
     bwd2cm_kernel<<<grid, 160, smem, st>>>(angles, spectrum, gout, gangles, partial, N, (N + CM_S - 1) / CM_S);
     return int(cudaGetLastError());
 }
+
+// ===================================================================== warp-specialised, degree-pipelined backward
+// warps 0-4: math (thread = (sample, channel), 16 samples x 10 channels); warp 5: service warp that, per degree,
+// sums the finished gradient rows over the 16 samples and immediately refills them with the next tile's rows.
+// The math warps never wait for a whole-tile load or a reduce phase.
+constexpr int WS_S = 16;
+constexpr int WS_MATH = 160;
+constexpr int WS_NSVC = 2;                 // service warps
+constexpr int WS_THREADS = WS_MATH + 32 * WS_NSVC;
+constexpr int WS_SL = 32 * WS_NSVC;        // service lanes
+
+__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void mbar_cp_async_arrive(uint64_t* bar) { asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+struct WsShared {
+    float* tile; float* trig; float* gp; float* acc; float* item; uint64_t* g_ready; uint64_t* trig_ready;
+};
+
+template <int L>
+__device__ __forceinline__ void ws_math_degrees(const WsShared& sh, const float* srow, float* trow, const float2* tg, uint32_t parity,
+                                                float& ga, float& gb, float& gc) {
+    mbar_wait(sh.g_ready + L, parity);                       // rows of degree L of this tile have landed
+    degree_bwd<L, 0>(srow + L * L * C, trow + L * L * C, tg, ga, gb, gc);
+    bar_arrive(1 + L, WS_THREADS);                            // gradient rows of degree L are final
+    if constexpr (L < LMAX) ws_math_degrees<L + 1>(sh, srow, trow, tg, parity, ga, gb, gc);
+}
+
+// service warp: issue the loads of the degree-L rows of tile at sample n0 (rows samples), 8-byte pieces
+template <int L>
+__device__ __forceinline__ void ws_load_degree(const WsShared& sh, const float* __restrict__ gout, int64_t n0, int rows, int lane) {
+    constexpr int PPS = (2 * L + 1) * (C / 2);                // 8-byte pieces per sample for this degree
+    const int total = rows * PPS;
+    for (int j = lane; j < total; j += WS_SL) {
+        const int s = j / PPS, k = j - s * PPS;
+        const int off = s * MC + L * L * C + 2 * k;
+        cp_async8(sh.tile + off, gout + n0 * MC + off);
+    }
+    mbar_cp_async_arrive(sh.g_ready + L);
+}
+template <int L>
+__device__ __forceinline__ void ws_service_degrees(const WsShared& sh, const float* __restrict__ gout, int rows, bool has_next, int64_t n_next,
+                                                   int rows_next, int lane) {
+    bar_sync(1 + L, WS_THREADS);                              // all math threads finished degree L
+    constexpr int NP = (2 * L + 1) * (C / 2);                 // column pairs of this degree
+    for (int p = lane; p < NP; p += WS_SL) {
+        const int col = L * L * C + 2 * p;
+        float2 a = *reinterpret_cast<float2*>(sh.acc + col);
+        for (int r = 0; r < rows; ++r) { const float2 u = *reinterpret_cast<const float2*>(sh.tile + r * MC + col); a.x += u.x; a.y += u.y; }
+        *reinterpret_cast<float2*>(sh.acc + col) = a;
+    }
+    bar_sync(12, WS_SL);                                      // all service lanes have summed this degree
+    if (has_next) ws_load_degree<L>(sh, gout, n_next, rows_next, lane);
+    if constexpr (L < LMAX) ws_service_degrees<L + 1>(sh, gout, rows, has_next, n_next, rows_next, lane);
+}
+template <int L>
+__device__ __forceinline__ void ws_load_all(const WsShared& sh, const float* __restrict__ gout, int64_t n0, int rows, int lane) {
+    ws_load_degree<L>(sh, gout, n0, rows, lane);
+    if constexpr (L < LMAX) ws_load_all<L + 1>(sh, gout, n0, rows, lane);
+}
+__device__ __forceinline__ void ws_trig(float* s_trig, const float* __restrict__ angles, int64_t n0, int rows, int lane) {
+    for (int j = lane; j < rows * 3; j += WS_SL) {
+        const int s = j / 3, a = j - 3 * s;
+        float s1, c1;
+        sincosf(__ldg(angles + n0 * 3 + j), &s1, &c1);
+        float2* dst = reinterpret_cast<float2*>(s_trig + s * TS + a * 16);
+        float cm = c1, sm = s1;
+#pragma unroll
+        for (int m = 1; m <= LMAX; ++m) { dst[m - 1] = make_float2(cm, sm); const float cn = fmaf(cm, c1, -(sm * s1)); sm = fmaf(sm, c1, cm * s1); cm = cn; }
+    }
+}
+
+__global__ void __launch_bounds__(WS_THREADS, 3)
+bwdws_kernel(const float* __restrict__ angles, const float* __restrict__ spectrum, const float* __restrict__ gout,
+             float* __restrict__ gangles, float* __restrict__ partial, int64_t N, int64_t ntiles) {
+    extern __shared__ __align__(16) float smem[];
+    WsShared sh;
+    sh.tile = smem;                                  // [16][810]
+    sh.trig = sh.tile + WS_S * MC;                   // [2][16][52]
+    sh.gp = sh.trig + 2 * WS_S * TS;                 // [160][3]
+    sh.acc = sh.gp + 2 * WS_MATH * 3;                // [810] (+2 pad)
+    sh.item = sh.acc + MC + 2;                       // [810] (+2 pad)
+    sh.g_ready = reinterpret_cast<uint64_t*>(sh.item + MC + 2);   // [9]
+    sh.trig_ready = sh.g_ready + 9;                  // [1]
+    const int t = threadIdx.x, warp = t >> 5, lane = t - WS_MATH;    // lane: index among the service lanes
+    for (int o = t; o < MC; o += blockDim.x) { sh.acc[o] = 0.f; sh.item[o] = __ldg(spectrum + o); }
+    if (t == 0) {
+        for (int l = 0; l <= LMAX; ++l) mbar_init(sh.g_ready + l, WS_SL);
+        mbar_init(sh.trig_ready, WS_SL);
+    }
+    __syncthreads();
+    const int64_t first = blockIdx.x, stride = gridDim.x;
+    if (warp < 5) {
+        // ---------------------------------------------------------------- math warps
+        const int s = t / C, c = t - s * C;
+        uint32_t it = 0;
+        for (int64_t tile_idx = first; tile_idx < ntiles; tile_idx += stride, ++it) {
+            const int64_t n0 = tile_idx * WS_S;
+            const int rows = int(min(int64_t(WS_S), N - n0));
+            const uint32_t parity = it & 1u;
+            mbar_wait(sh.trig_ready, parity);
+            float ga = 0.f, gb = 0.f, gc = 0.f;
+            if (s < rows) {
+                const float2* tg = reinterpret_cast<const float2*>(sh.trig + (it & 1u) * WS_S * TS + s * TS);
+                ws_math_degrees<0>(sh, sh.item + c, sh.tile + s * MC + c, tg, parity, ga, gb, gc);
+            } else {
+                // idle column (partial last tile): still take part in the per-degree hand-shake
+#pragma unroll
+                for (int l = 0; l <= LMAX; ++l) { mbar_wait(sh.g_ready + l, parity); bar_arrive(1 + l, WS_THREADS); }
+            }
+            float* gp = sh.gp + (it & 1u) * WS_MATH * 3;     // double-buffered: the service warp reads it a little later
+            gp[t * 3 + 0] = ga; gp[t * 3 + 1] = gb; gp[t * 3 + 2] = gc;
+            bar_arrive(10 + (it & 1u), WS_THREADS);          // angle-gradient parts are written
+        }
+    } else {
+        // ---------------------------------------------------------------- service warp
+        uint32_t it = 0;
+        if (first < ntiles) {
+            const int rows0 = int(min(int64_t(WS_S), N - first * WS_S));
+            ws_trig(sh.trig, angles, first * WS_S, rows0, lane);
+            mbar_arrive(sh.trig_ready);
+            ws_load_all<0>(sh, gout, first * WS_S, rows0, lane);
+        }
+        for (int64_t tile_idx = first; tile_idx < ntiles; tile_idx += stride, ++it) {
+            const int64_t n0 = tile_idx * WS_S;
+            const int rows = int(min(int64_t(WS_S), N - n0));
+            const int64_t nxt = tile_idx + stride;
+            const bool has_next = nxt < ntiles;
+            const int64_t n_next = nxt * WS_S;
+            const int rows_next = has_next ? int(min(int64_t(WS_S), N - n_next)) : 0;
+            if (has_next) {
+                ws_trig(sh.trig + ((it + 1) & 1u) * WS_S * TS, angles, n_next, rows_next, lane);
+                mbar_arrive(sh.trig_ready);
+            }
+            ws_service_degrees<0>(sh, gout, rows, has_next, n_next, rows_next, lane);
+            bar_sync(10 + (it & 1u), WS_THREADS);
+            const float* gp = sh.gp + (it & 1u) * WS_MATH * 3;
+            for (int j = lane; j < rows * 3; j += WS_SL) {
+                const int ss = j / 3, a = j - 3 * ss;
+                float sum = 0.f;
+#pragma unroll
+                for (int cc = 0; cc < C; ++cc) sum += gp[(ss * C + cc) * 3 + a];
+                gangles[n0 * 3 + j] = sum;
+            }
+        }
+    }
+    __syncthreads();
+    for (int o = t; o < MC; o += blockDim.x) partial[int64_t(blockIdx.x) * MC + o] = sh.acc[o];
+}
+
+extern "C" int exp_wigner_bwdws(const float* angles, const float* spectrum, const float* gout, float* gangles, float* partial,
+                                int64_t N, int grid, void* stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t smem = size_t(WS_S * MC + 2 * WS_S * TS + 2 * WS_MATH * 3 + MC + 2 + MC + 2) * 4 + 10 * 8;
+    cudaError_t e = cudaFuncSetAttribute(bwdws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return int(e);
+    bwdws_kernel<<<grid, WS_THREADS, smem, st>>>(angles, spectrum, gout, gangles, partial, N, (N + WS_S - 1) / WS_S);
+    return int(cudaGetLastError());
+}
