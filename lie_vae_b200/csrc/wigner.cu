@@ -329,6 +329,141 @@ wigner_bwd_kernel(const float* __restrict__ angles, const float* __restrict__ sp
         for (int o = t; o < MC; o += blockDim.x) partial[int64_t(blockIdx.x) * MC + o] = s_acc[o];
 }
 
+// ------------------------------------------------------------------ backward, shared spectrum, TMA-fed (sm_100a)
+// One persistent CTA per SM with three math groups of 160 threads and four 16-sample tile buffers.  Tile j of the CTA
+// lives in buffer j % 4 and is processed by group j % 3.  A group that has finished a tile hands it to the copy engine
+// twice: a TMA bulk reduce-add (cp.reduce.async.bulk ... add.f32; the group's first tile is a plain bulk store) of the
+// gradient rows into the group's own fp32 accumulator in global memory, then a TMA bulk load of tile j + 4 into the same
+// buffer, completing on the buffer's mbarrier.  Three tiles are always being computed while the fourth is in flight, so
+// the math groups never execute a copy loop or a reduction loop and never wait for HBM in steady state.  Each accumulator
+// element receives exactly one add per tile, in tile order: the batch sum stays run-to-run reproducible.
+// Requires full 16-sample tiles and 16-byte aligned g_y (the host sends a ragged tail through wigner_bwd_kernel).
+constexpr int WQ_S = 16, WQ_GROUPS = 3, WQ_BUFS = 4, WQ_GT = 160, WQ_THREADS = WQ_GROUPS * WQ_GT;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}"
+                 ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int CT, int LT>
+__global__ void __launch_bounds__(WQ_THREADS, 1)
+wigner_bwd_tma_kernel(const float* __restrict__ angles, const float* __restrict__ spectrum, const float* __restrict__ gout,
+                      float* __restrict__ gangles, float* __restrict__ gacc, int64_t ntiles, int transpose) {
+    constexpr int C = CT, M = (LT + 1) * (LT + 1), MC = M * C;
+    constexpr uint32_t TILE_BYTES = WQ_S * MC * 4u;
+    extern __shared__ __align__(16) float smem[];
+    float* tiles = smem;                                          // [4][16][MC]
+    float* trig_all = tiles + WQ_BUFS * WQ_S * MC;                 // [3][16][52]
+    float* gp_all = trig_all + WQ_GROUPS * WQ_S * WG_TRIG_STRIDE;  // [3][160][3]
+    uint64_t* full = reinterpret_cast<uint64_t*>(gp_all + WQ_GROUPS * WQ_GT * 3);   // [4]
+    const int tid = threadIdx.x, g = tid / WQ_GT, t = tid - g * WQ_GT;
+    const int s = t / C, c = t - s * C;
+    float* s_trig = trig_all + g * WQ_S * WG_TRIG_STRIDE;
+    float* s_gp = gp_all + g * WQ_GT * 3;
+    // tiles of this CTA: blockIdx.x + j * gridDim.x, j = 0, 1, ...
+    const int64_t first = blockIdx.x, stride = gridDim.x;
+    const int64_t my_tiles = first < ntiles ? (ntiles - first + stride - 1) / stride : 0;
+    float* acc = gacc + (int64_t(blockIdx.x) * WQ_GROUPS + g) * WQ_S * MC;
+    if (tid == 0) {
+        for (int b = 0; b < WQ_BUFS; ++b) mbar_init(full + b, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int j = 0; j < WQ_BUFS && j < my_tiles; ++j) {
+            mbar_expect_tx(full + j, TILE_BYTES);
+            tma_load(tiles + j * WQ_S * MC, gout + (first + j * stride) * WQ_S * MC, TILE_BYTES, full + j);
+        }
+    }
+    if (g >= my_tiles)      // a group without work still owns an accumulator that the final reduction reads
+        for (int o = t; o < WQ_S * MC; o += WQ_GT) acc[o] = 0.f;
+    for (int64_t j = g; j < my_tiles; j += WQ_GROUPS) {
+        const int buf = int(j % WQ_BUFS);
+        const uint32_t parity = uint32_t(j / WQ_BUFS) & 1u;
+        const int64_t n0 = (first + j * stride) * WQ_S;
+        float* tile = tiles + buf * WQ_S * MC;
+        // trig table of this tile (group-private), then wait for the tile itself
+        for (int q = t; q < WQ_S * 3; q += WQ_GT) {
+            const int ss = q / 3, a = q - 3 * ss;
+            const float phi = transpose ? -__ldg(angles + (n0 + ss) * 3 + (2 - a)) : __ldg(angles + n0 * 3 + q);
+            float s1, c1;
+            sincosf(phi, &s1, &c1);
+            float2* dst = reinterpret_cast<float2*>(s_trig + ss * WG_TRIG_STRIDE + a * (2 * WG_LMAX));
+            float cm = c1, sm = s1;
+#pragma unroll
+            for (int m = 1; m <= WG_LMAX; ++m) {
+                dst[m - 1] = make_float2(cm, sm);
+                const float cn = fmaf(cm, c1, -(sm * s1));
+                sm = fmaf(sm, c1, cm * s1);
+                cm = cn;
+            }
+        }
+        mbar_wait(full + buf, parity);
+        named_bar_sync(1 + g, WQ_GT);
+        {
+            float ga = 0.f, gb = 0.f, gc = 0.f;
+            bwd_unrolled<0, LT, true>(spectrum + c, tile + s * MC + c, C, reinterpret_cast<const float2*>(s_trig + s * WG_TRIG_STRIDE), ga, gb, gc);
+            s_gp[t * 3 + 0] = transpose ? -gc : ga;
+            s_gp[t * 3 + 1] = transpose ? -gb : gb;
+            s_gp[t * 3 + 2] = transpose ? -ga : gc;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy tile writes -> visible to the copy engine
+        named_bar_sync(1 + g, WQ_GT);
+        if (t == 0) {
+            if (j == g)
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             :: "l"(acc), "r"(smem_u32(tile)), "r"(TILE_BYTES) : "memory");
+            else
+                asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                             :: "l"(acc), "r"(smem_u32(tile)), "r"(TILE_BYTES) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the engine has read the buffer: refill it
+            const int64_t jn = j + WQ_BUFS;
+            if (jn < my_tiles) {
+                mbar_expect_tx(full + buf, TILE_BYTES);
+                tma_load(tile, gout + (first + jn * stride) * WQ_S * MC, TILE_BYTES, full + buf);
+            }
+        }
+        for (int q = t; q < WQ_S * 3; q += WQ_GT) {
+            const int ss = q / 3, a = q - 3 * ss;
+            float sum = 0.f;
+#pragma unroll
+            for (int cc = 0; cc < C; ++cc) sum += s_gp[(ss * C + cc) * 3 + a];
+            gangles[n0 * 3 + q] = sum;
+        }
+    }
+    if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all bulk reductions done before the grid retires
+}
+
+// rows [r0, r0 + chunk) of partial [nrows][MC] -> out[blockIdx.y][MC]   (first pass of the row reduction)
+__global__ void __launch_bounds__(256)
+wigner_reduce_chunks(const float* __restrict__ partial, float* __restrict__ out, int nrows, int chunk, int MC) {
+    __shared__ float red[8][33];
+    const int o = blockIdx.x * 32 + threadIdx.x;
+    const int r0 = blockIdx.y * chunk, r1 = min(nrows, r0 + chunk);
+    float acc = 0.f;
+    if (o < MC)
+        for (int b = r0 + threadIdx.y; b < r1; b += 8) acc += partial[int64_t(b) * MC + o];
+    red[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && o < MC) {
+        float a = 0.f;
+#pragma unroll
+        for (int y = 0; y < 8; ++y) a += red[y][threadIdx.x];
+        out[int64_t(blockIdx.y) * MC + o] = a;
+    }
+}
+
 // partial [nblk][MC] -> out[MC]; block = (32, 8): 32 consecutive columns, 8-way split over rows.
 __global__ void __launch_bounds__(256)
 wigner_reduce_partials(const float* __restrict__ partial, float* __restrict__ out, int nblk, int MC) {
@@ -430,6 +565,52 @@ static int launch_bwd(const WgGeom& g, const float* angles, const float* spectru
     return check_launch("wigner_apply_bwd");
 }
 
+// ---- TMA-fed backward (shared spectrum, C = 10, degrees 0..8 or 0..6, 16-byte aligned g_y) -------------------------
+constexpr int WQ_CHUNK = 128;      // rows per block in the first pass of the final row reduction
+
+static bool tma_bwd_eligible(int C, int lmin, int lmax, const float* gout, int64_t N) {
+    return C == 10 && lmin == 0 && (lmax == 8 || lmax == 6) && N >= WQ_S && (reinterpret_cast<uintptr_t>(gout) & 15u) == 0;
+}
+// workspace rows (of MC floats): accumulators [sms*3*16] | tail partial [1] | chunk sums [ceil(rows / WQ_CHUNK)]
+static int64_t tma_bwd_workspace_rows(int sms) {
+    const int64_t rows = int64_t(sms) * WQ_GROUPS * WQ_S + 1;
+    return rows + (rows + WQ_CHUNK - 1) / WQ_CHUNK;
+}
+
+template <int LT>
+static int launch_bwd_tma(const WgGeom& g, const float* angles, const float* spectrum, const float* gout, float* gangles,
+                          float* gspectrum, float* workspace, int64_t workspace_floats, int64_t N, int transpose, cudaStream_t st) {
+    constexpr int C = 10, MC = (LT + 1) * (LT + 1) * C;
+    if (!workspace || workspace_floats < tma_bwd_workspace_rows(g.sms) * MC) {
+        set_error("wigner_apply_bwd: workspace of %lld floats required", (long long)(tma_bwd_workspace_rows(g.sms) * MC));
+        return LV_ERR_ARG;
+    }
+    const int64_t ntiles = N / WQ_S, n_full = ntiles * WQ_S, n_tail = N - n_full;
+    const int grid = int(ntiles < g.sms ? ntiles : g.sms);
+    const size_t smem = size_t(WQ_BUFS * WQ_S * MC + WQ_GROUPS * WQ_S * WG_TRIG_STRIDE + WQ_GROUPS * WQ_GT * 3) * 4 + WQ_BUFS * 8;
+    int rc = opt_in_smem(wigner_bwd_tma_kernel<C, LT>, smem);
+    if (rc) return rc;
+    wigner_bwd_tma_kernel<C, LT><<<grid, WQ_THREADS, smem, st>>>(angles, spectrum, gout, gangles, workspace, ntiles, transpose);
+    if ((rc = check_launch("wigner_apply_bwd (tma)"))) return rc;
+    int rows = grid * WQ_GROUPS * WQ_S;
+    if (n_tail > 0) {
+        // ragged tail (< 16 samples): the cp.async kernel, one CTA, its partial row goes right after the accumulators
+        WgGeom gt = g;
+        gt.ntiles = (n_tail + g.S - 1) / g.S;
+        int tail_grid = 0;
+        rc = launch_bwd<true, 0, -1>(gt, angles + n_full * 3, spectrum, gout + n_full * MC, gangles + n_full * 3, nullptr,
+                                     workspace + int64_t(rows) * MC, int64_t(gt.ntiles) * MC, n_tail, 0, LT, C, transpose, st, &tail_grid);
+        if (rc) return rc;
+        rows += tail_grid;
+    }
+    const int nchunks = (rows + WQ_CHUNK - 1) / WQ_CHUNK;
+    float* chunk_sums = workspace + int64_t(rows) * MC;
+    wigner_reduce_chunks<<<dim3((MC + 31) / 32, nchunks), dim3(32, 8), 0, st>>>(workspace, chunk_sums, rows, WQ_CHUNK, MC);
+    if ((rc = check_launch("wigner_reduce_chunks"))) return rc;
+    wigner_reduce_partials<<<(MC + 31) / 32, dim3(32, 8), 0, st>>>(chunk_sums, gspectrum, nchunks, MC);
+    return check_launch("wigner_reduce_partials");
+}
+
 }  // namespace lv
 
 // compile-time specialisations: 10 channels (ActionNet default, decoders.py:11 / main.py:168) with degrees
@@ -444,7 +625,12 @@ extern "C" int64_t lv_wigner_bwd_workspace_floats(int64_t N, int lmin, int lmax,
     lv::WgGeom g;
     if (lv::wigner_geometry("wigner_bwd_workspace", N, lmin, lmax, C, true, g) != LV_OK) return -1;
     const int64_t cap = int64_t(g.sms) * lv::WG_MAX_CTAS_PER_SM;
-    return (g.ntiles < cap ? g.ntiles : cap) * g.MC;
+    int64_t rows = g.ntiles < cap ? g.ntiles : cap;
+    if (C == 10 && lmin == 0 && (lmax == 8 || lmax == 6) && N >= lv::WQ_S) {
+        const int64_t tma_rows = lv::tma_bwd_workspace_rows(g.sms);
+        if (tma_rows > rows) rows = tma_rows;
+    }
+    return rows * g.MC;
 }
 
 extern "C" int lv_wigner_apply_fwd_f32(const float* angles, const float* spectrum, float* out, int64_t N, int lmin,
@@ -476,6 +662,10 @@ extern "C" int lv_wigner_apply_bwd_f32(const float* angles, const float* spectru
     }
     if (!angles || !spectrum || !gout || !gangles) { lv::set_error("wigner_apply_bwd: null pointer"); return LV_ERR_ARG; }
     int grid = 0;
+    if (shared_spectrum && lv::tma_bwd_eligible(C, lmin, lmax, gout, N)) {
+        if (lmax == 8) return lv::launch_bwd_tma<8>(g, angles, spectrum, gout, gangles, gspectrum, workspace, workspace_floats, N, transpose, st);
+        return lv::launch_bwd_tma<6>(g, angles, spectrum, gout, gangles, gspectrum, workspace, workspace_floats, N, transpose, st);
+    }
     if (shared_spectrum) {
         rc = WG_DISPATCH(C, lmin, lmax, true, lv::launch_bwd, g, angles, spectrum, gout, gangles, gspectrum, workspace, workspace_floats, N, lmin, lmax, C, transpose, st, &grid);
         if (rc) return rc;

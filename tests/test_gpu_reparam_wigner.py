@@ -291,3 +291,38 @@ def test_wigner_errors(mods):
     with pytest.raises(AssertionError):
         dc.ActionNet(2, torch.nn.Sequential()).cuda()(torch.randn(4, 4, device="cuda"))
     assert lt.block_wigner_matrix_multiply(torch.empty(0, 3, device="cuda"), torch.empty(0, 9, 2, device="cuda"), 2).shape == (0, 9, 2)
+
+
+@pytest.mark.parametrize("L", [8, 6])
+@pytest.mark.parametrize("N", [16, 17, 31, 48, 49, 16 * 150 + 3, 16 * 600])
+@pytest.mark.parametrize("tr", [False, True])
+def test_tma_backward_matches_cp_async_backward(mods, L, N, tr):
+    """The TMA-fed backward (C = 10, degrees 0..8 / 0..6, 16-byte aligned g_y) against the cp.async kernel, which
+    the same call falls back to when g_y is only 4-byte aligned; and against the oracle for the small sizes."""
+    from lie_vae_b200 import _ops
+    torch.manual_seed(N + L)
+    M, C = (L + 1) ** 2, 10
+    ang = O.group_matrix_to_eazyz(O.random_group_matrices(N, dtype=torch.float64)).float().cuda()
+    item = torch.randn(M, C, device="cuda")
+    g_aligned = torch.randn(N, M, C, device="cuda")
+    g_unaligned = torch.empty(N * M * C + 1, device="cuda")[1:].view(N, M, C)
+    g_unaligned.copy_(g_aligned)
+    assert g_aligned.data_ptr() % 16 == 0 and g_unaligned.data_ptr() % 16 != 0
+
+    def run(g):
+        a, it = ang.clone().requires_grad_(True), item.clone().requires_grad_(True)
+        out = _ops.WignerApply.apply(a, it, 0, L, tr)
+        out.backward(g)
+        return a.grad, it.grad
+    ga1, gi1 = run(g_aligned)
+    ga2, gi2 = run(g_unaligned)
+    assert torch.equal(ga1, ga2)                                   # per-sample math is identical
+    scale = gi2.abs().max().item()
+    assert (gi1 - gi2).abs().max().item() <= 2e-6 * scale          # only the summation order differs
+    ga1b, gi1b = run(g_aligned)
+    assert torch.equal(gi1, gi1b) and torch.equal(ga1, ga1b)        # run-to-run reproducible
+    if N <= 64:
+        a64, it64 = ang.double().cpu().requires_grad_(True), item.double().cpu().requires_grad_(True)
+        (O.action_net_forward(a64, it64, L, tr) * g_aligned.double().cpu().view(N, -1)).sum().backward()
+        close(gi1, it64.grad, 1e-5, 1e-5 * max(1.0, scale))
+        close(ga1, a64.grad, 2e-5, 1e-4)

@@ -44,6 +44,35 @@ if __name__ == "__main__":
     ref = lt.block_wigner_matrix_multiply(ang, item.expand(B, -1, -1), L).view(B, -1)
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     P = lambda t: ctypes.c_void_p(t.data_ptr())
+    if sys.argv[1] == "bwdq":
+        gy = [torch.randn(B, M * C, device=dev) for _ in range(3)]
+        gang = torch.empty(B, 3, device=dev)
+        gacc = torch.zeros(148 * 3 * 16 * M * C, device=dev)
+        import lie_vae_b200._ops as ops
+        a_ref = ang.clone().requires_grad_(True)
+        it_ref = item.clone().requires_grad_(True)
+        (ops.WignerApply.apply(a_ref, it_ref, 0, L, False).view(B, -1) * gy[0]).sum().backward()
+        def run(i):
+            rc = lib.exp_wigner_bwdq(P(ang), P(item), P(gy[i % 3]), P(gang), P(gacc), ctypes.c_int64(B), 148, st)
+            assert rc == 0, rc
+        run(0); torch.cuda.synchronize()
+        gi = gacc.view(-1, M, C).sum(0)
+        run(0); torch.cuda.synchronize()
+        gi2 = gacc.view(-1, M, C).sum(0)
+        err_a = float((gang - a_ref.grad).abs().max())
+        err_i = float((gi - it_ref.grad).abs().max() / it_ref.grad.abs().max())
+        for i in range(3):
+            run(i)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(20):
+            run(i)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 20
+        print("bwdq: %.4f ms (incl. memset)  %.0f GB/s  err_angles %.2e err_item(rel) %.2e repeat_equal %s" % (ms, 3264 * B / ms / 1e6, err_a, err_i, bool(torch.equal(gi, gi2))), flush=True)
+        raise SystemExit(0)
     if sys.argv[1] in ("bwdcm", "bwd2cm", "bwdws"):
         gy = [torch.randn(B, M * C, device=dev) for _ in range(3)]
         gang = torch.empty(B, 3, device=dev)
@@ -139,7 +168,12 @@ if __name__ == "__main__":
     if sys.argv[1] == "bwd":
         gy = [torch.randn(B, M * C, device=dev) for _ in range(3)]
         gang = torch.empty(B, 3, device=dev)
-        part = torch.empty(148 * 6 * M * C, device=dev)
+        part = torch.zeros(148 * 4 * 16 * M * C, device=dev)
+        import lie_vae_b200._ops as ops
+        gy0 = gy[0]
+        a_ref = ang.clone().requires_grad_(True)
+        it_ref = item.clone().requires_grad_(True)
+        (ops.WignerApply.apply(a_ref, it_ref, 0, L, False).view(B, -1) * gy0).sum().backward()
         for var in [int(v) for v in sys.argv[2].split(",")]:
             for S in [int(v) for v in sys.argv[3].split(",")]:
                 for gm in [int(v) for v in sys.argv[4].split(",")]:
@@ -156,7 +190,15 @@ if __name__ == "__main__":
                     b.record()
                     torch.cuda.synchronize()
                     ms = a.elapsed_time(b) / 20
-                    print("bwd var %3d S %2d grid 148x%d: %.4f ms  %.0f GB/s  chk %.4f" % (var, S, gm, ms, 3264 * B / ms / 1e6, float(gang.abs().mean())), flush=True)
+                    extra = ""
+                    if var & 128:
+                        part.zero_(); run(0); torch.cuda.synchronize()
+                        gi = part[:148 * gm * S * M * C].view(-1, M, C).sum(0)
+                        gi2 = None
+                        part.zero_(); run(0); torch.cuda.synchronize()
+                        gi2 = part[:148 * gm * S * M * C].view(-1, M, C).sum(0)
+                        extra = " err_item(rel) %.2e repeat_equal %s" % (float((gi - it_ref.grad).abs().max() / it_ref.grad.abs().max()), bool(torch.equal(gi, gi2)))
+                    print("bwd var %3d S %2d grid 148x%d: %.4f ms  %.0f GB/s  chk %.4f%s" % (var, S, gm, ms, 3264 * B / ms / 1e6, float(gang.abs().mean()), extra), flush=True)
         raise SystemExit(0)
     for var in [int(v) for v in sys.argv[1].split(",")]:
         for S in [int(v) for v in sys.argv[2].split(",")]:

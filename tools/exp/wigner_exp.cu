@@ -242,8 +242,23 @@ bwd_kernel(const float* __restrict__ angles, const float* __restrict__ spectrum,
             degrees_bwd_from<0, BV>(srow, trow, tg, ga, gb, gc);
             s_gp[t * 3 + 0] = ga; s_gp[t * 3 + 1] = gb; s_gp[t * 3 + 2] = gc;
         }
+        if (BV & 128) {
+            // TMA bulk reduce-add: the copy engine adds the whole tile into this CTA's fp32 accumulator in global
+            // memory (L2); the SM only fences, issues one instruction and waits for the smem read.
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (t == 0) {
+                float* gacc = partial + int64_t(blockIdx.x) * S * MC;
+                asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                             :: "l"(gacc), "r"(uint32_t(__cvta_generic_to_shared(tile))), "r"(uint32_t(rows) * MC * 4u) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+        } else {
         __syncthreads();
-        if (BV & 32) {
+        }
+        if (BV & 128) {
+        } else if (BV & 32) {
             // 128-bit column sums: 202 float4 columns + one float2 tail (MC = 810)
             for (int q = t; q < 203; q += blockDim.x) {
                 if (q < 202) {
@@ -278,7 +293,7 @@ bwd_kernel(const float* __restrict__ angles, const float* __restrict__ spectrum,
         }
         __syncthreads();
     }
-    for (int o = t; o < MC; o += blockDim.x) partial[int64_t(blockIdx.x) * MC + o] = s_acc[o];
+    if (!(BV & 128)) for (int o = t; o < MC; o += blockDim.x) partial[int64_t(blockIdx.x) * MC + o] = s_acc[o];
 }
 
 template <int BV, int MINB>
@@ -302,6 +317,9 @@ extern "C" int exp_wigner_bwd(int var, const float* angles, const float* spectru
         case 16: return launch_b<16, 3>(angles, spectrum, gout, gangles, partial, N, S, grid, st);
         case 32: return launch_b<32, 3>(angles, spectrum, gout, gangles, partial, N, S, grid, st);
         case 48: return launch_b<48, 3>(angles, spectrum, gout, gangles, partial, N, S, grid, st);
+        case 129: return launch_b<129, 3>(angles, spectrum, gout, gangles, partial, N, S, grid, st);
+        case 160: return launch_b<160, 3>(angles, spectrum, gout, gangles, partial, N, S, grid, st);
+        case 128: return launch_b<128, 3>(angles, spectrum, gout, gangles, partial, N, S, grid, st);
         case 96: return launch_b<96, 3>(angles, spectrum, gout, gangles, partial, N, S, grid, st);
         case 100: return launch_b<0, 4>(angles, spectrum, gout, gangles, partial, N, S, grid, st);
         default: return -1;
@@ -945,5 +963,111 @@ extern "C" int exp_wigner_bwdws(const float* angles, const float* spectrum, cons
     cudaError_t e = cudaFuncSetAttribute(bwdws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return int(e);
     bwdws_kernel<<<grid, WS_THREADS, smem, st>>>(angles, spectrum, gout, gangles, partial, N, (N + WS_S - 1) / WS_S);
+    return int(cudaGetLastError());
+}
+
+// ===================================================================== one persistent CTA per SM, 3 math groups, 4 tile buffers
+// Tile j of this CTA lives in buffer j % 4 and is processed by group j % 3.  A group that finishes a tile hands it to the
+// copy engine twice: a TMA bulk reduce-add of the gradient rows into the group's fp32 accumulator in global memory (L2),
+// then a TMA bulk load of tile j + 4 into the same buffer.  Three tiles are always being computed while the fourth loads.
+constexpr int Q_GROUPS = 3, Q_BUFS = 4, Q_GT = 160, Q_THREADS = Q_GROUPS * Q_GT;
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(Q_THREADS, 1)
+bwdq_kernel(const float* __restrict__ angles, const float* __restrict__ spectrum, const float* __restrict__ gout,
+            float* __restrict__ gangles, float* __restrict__ gacc, int64_t N, int64_t ntiles) {
+    extern __shared__ __align__(16) float smem[];
+    float* tiles = smem;                                          // [4][16][810]
+    float* trig_all = tiles + Q_BUFS * WS_S * MC;                  // [3][16][52]
+    float* gp_all = trig_all + Q_GROUPS * WS_S * TS;               // [3][160][3]
+    uint64_t* full = reinterpret_cast<uint64_t*>(gp_all + Q_GROUPS * Q_GT * 3);   // [4]
+    const int tid = threadIdx.x, g = tid / Q_GT, t = tid - g * Q_GT;
+    const int s = t / C, c = t - s * C;
+    float* s_trig = trig_all + g * WS_S * TS;
+    float* s_gp = gp_all + g * Q_GT * 3;
+    // tiles of this CTA: blockIdx.x + j * gridDim.x, j = 0, 1, ...
+    const int64_t first = blockIdx.x, stride = gridDim.x;
+    const int64_t my_tiles = first < ntiles ? (ntiles - first + stride - 1) / stride : 0;
+    if (tid == 0) {
+        for (int b = 0; b < Q_BUFS; ++b) mbar_init(full + b, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int j = 0; j < Q_BUFS && j < my_tiles; ++j) {
+            const int64_t n0 = (first + j * stride) * WS_S;
+            const uint32_t bytes = uint32_t(min(int64_t(WS_S), N - n0)) * MC * 4u;
+            mbar_expect_tx(full + j, bytes);
+            bulk_load(tiles + j * WS_S * MC, gout + n0 * MC, bytes, full + j);
+        }
+    }
+    for (int64_t j = g; j < my_tiles; j += Q_GROUPS) {
+        const int buf = int(j % Q_BUFS);
+        const uint32_t parity = uint32_t(j / Q_BUFS) & 1u;
+        const int64_t n0 = (first + j * stride) * WS_S;
+        const int rows = int(min(int64_t(WS_S), N - n0));
+        float* tile = tiles + buf * WS_S * MC;
+        // trig table of this tile (group-private), then wait for the tile itself
+        for (int q = t; q < rows * 3; q += Q_GT) {
+            const int ss = q / 3, a = q - 3 * ss;
+            float s1, c1;
+            sincosf(__ldg(angles + n0 * 3 + q), &s1, &c1);
+            float2* dst = reinterpret_cast<float2*>(s_trig + ss * TS + a * 16);
+            float cm = c1, sm = s1;
+#pragma unroll
+            for (int m = 1; m <= LMAX; ++m) { dst[m - 1] = make_float2(cm, sm); const float cn = fmaf(cm, c1, -(sm * s1)); sm = fmaf(sm, c1, cm * s1); cm = cn; }
+        }
+        mbar_wait(full + buf, parity);
+        bar_sync(1 + g, Q_GT);
+        if (s < rows) {
+            float ga = 0.f, gb = 0.f, gc = 0.f;
+            degrees_bwd_from<0, 8>(spectrum + c, tile + s * MC + c, reinterpret_cast<const float2*>(s_trig + s * TS), ga, gb, gc);
+            s_gp[t * 3 + 0] = ga; s_gp[t * 3 + 1] = gb; s_gp[t * 3 + 2] = gc;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        bar_sync(1 + g, Q_GT);
+        if (t == 0) {
+            const uint32_t bytes = uint32_t(rows) * MC * 4u;
+            float* acc = gacc + (int64_t(blockIdx.x) * Q_GROUPS + g) * WS_S * MC;
+            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                         :: "l"(acc), "r"(smem_u32(tile)), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            const int64_t jn = j + Q_BUFS;
+            if (jn < my_tiles) {
+                const int64_t nn = (first + jn * stride) * WS_S;
+                const uint32_t nb = uint32_t(min(int64_t(WS_S), N - nn)) * MC * 4u;
+                mbar_expect_tx(full + buf, nb);
+                bulk_load(tile, gout + nn * MC, nb, full + buf);
+            }
+        }
+        for (int q = t; q < rows * 3; q += Q_GT) {
+            const int ss = q / 3, a = q - 3 * ss;
+            float sum = 0.f;
+#pragma unroll
+            for (int cc = 0; cc < C; ++cc) sum += s_gp[(ss * C + cc) * 3 + a];
+            gangles[n0 * 3 + q] = sum;
+        }
+    }
+    // all bulk reductions of this CTA must have completed before the kernel ends
+    if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+extern "C" int exp_wigner_bwdq(const float* angles, const float* spectrum, const float* gout, float* gangles, float* gacc,
+                               int64_t N, int grid, void* stream) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t smem = size_t(Q_BUFS * WS_S * MC + Q_GROUPS * WS_S * TS + Q_GROUPS * Q_GT * 3) * 4 + Q_BUFS * 8;
+    cudaError_t e = cudaFuncSetAttribute(bwdq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e != cudaSuccess) return int(e);
+    e = cudaMemsetAsync(gacc, 0, size_t(grid) * Q_GROUPS * WS_S * MC * 4, st);
+    if (e != cudaSuccess) return int(e);
+    bwdq_kernel<<<grid, Q_THREADS, smem, st>>>(angles, spectrum, gout, gangles, gacc, N, (N + WS_S - 1) / WS_S);
     return int(cudaGetLastError());
 }
