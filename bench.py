@@ -342,7 +342,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": n_loc * 60, "d2h_bytes_per_step": 4 * (1 + M * CHANNELS),
                     "api": "so3_reparameterize -> group_matrix_to_eazyz -> WignerApply (autograd), pinned host mu/sigma/eps, double-buffered copies"},
             "gpu_launches": (step_obj.LAUNCHES_PER_MICROBATCH * n_micro + step_obj.LAUNCHES_PER_SHARD) * args.steps,
-            "roofline": {"bound": "hbm", "kernel": "wigner_bwd_kernel<shared,10,8>", "achieved": kernels[dom]["gbs"], "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "wigner_bwd_tma_kernel<10,8> (+ row-reduction kernels)", "achieved": kernels[dom]["gbs"], "peak": peak,
                          "unit": "GB/s", "frac": kernels[dom]["frac"],
                          # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture
                          # profiles/r01_ncu_wigner_v2_summary.txt (852.63 MB + 7.61 MB at 2^18 samples per launch)

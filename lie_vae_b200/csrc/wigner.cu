@@ -365,7 +365,10 @@ wigner_bwd_tma_kernel(const float* __restrict__ angles, const float* __restrict_
     float* tiles = smem;                                          // [4][16][MC]
     float* trig_all = tiles + WQ_BUFS * WQ_S * MC;                 // [3][16][52]
     float* gp_all = trig_all + WQ_GROUPS * WQ_S * WG_TRIG_STRIDE;  // [3][160][3]
-    uint64_t* full = reinterpret_cast<uint64_t*>(gp_all + WQ_GROUPS * WQ_GT * 3);   // [4]
+    // full[buf][use & 1]: two mbarriers per buffer, alternating between consecutive uses of the buffer.  With a single
+    // barrier per buffer a group that runs two uses ahead of a starved group would see the 1-bit phase parity of the
+    // previous use and walk into a buffer that is still being computed on.
+    uint64_t* full = reinterpret_cast<uint64_t*>(gp_all + WQ_GROUPS * WQ_GT * 3);   // [4][2]
     const int tid = threadIdx.x, g = tid / WQ_GT, t = tid - g * WQ_GT;
     const int s = t / C, c = t - s * C;
     float* s_trig = trig_all + g * WQ_S * WG_TRIG_STRIDE;
@@ -375,21 +378,23 @@ wigner_bwd_tma_kernel(const float* __restrict__ angles, const float* __restrict_
     const int64_t my_tiles = first < ntiles ? (ntiles - first + stride - 1) / stride : 0;
     float* acc = gacc + (int64_t(blockIdx.x) * WQ_GROUPS + g) * WQ_S * MC;
     if (tid == 0) {
-        for (int b = 0; b < WQ_BUFS; ++b) mbar_init(full + b, 1);
+        for (int b = 0; b < 2 * WQ_BUFS; ++b) mbar_init(full + b, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (tid == 0) {
         for (int j = 0; j < WQ_BUFS && j < my_tiles; ++j) {
-            mbar_expect_tx(full + j, TILE_BYTES);
-            tma_load(tiles + j * WQ_S * MC, gout + (first + j * stride) * WQ_S * MC, TILE_BYTES, full + j);
+            mbar_expect_tx(full + 2 * j, TILE_BYTES);          // use 0 of buffer j
+            tma_load(tiles + j * WQ_S * MC, gout + (first + j * stride) * WQ_S * MC, TILE_BYTES, full + 2 * j);
         }
     }
     if (g >= my_tiles)      // a group without work still owns an accumulator that the final reduction reads
         for (int o = t; o < WQ_S * MC; o += WQ_GT) acc[o] = 0.f;
     for (int64_t j = g; j < my_tiles; j += WQ_GROUPS) {
         const int buf = int(j % WQ_BUFS);
-        const uint32_t parity = uint32_t(j / WQ_BUFS) & 1u;
+        const int64_t use = j / WQ_BUFS;                       // how often this buffer has been filled before
+        uint64_t* bar = full + 2 * buf + int(use & 1);
+        const uint32_t parity = uint32_t(use >> 1) & 1u;
         const int64_t n0 = (first + j * stride) * WQ_S;
         float* tile = tiles + buf * WQ_S * MC;
         // trig table of this tile (group-private), then wait for the tile itself
@@ -408,7 +413,7 @@ wigner_bwd_tma_kernel(const float* __restrict__ angles, const float* __restrict_
                 cm = cn;
             }
         }
-        mbar_wait(full + buf, parity);
+        mbar_wait(bar, parity);
         named_bar_sync(1 + g, WQ_GT);
         {
             float ga = 0.f, gb = 0.f, gc = 0.f;
@@ -419,7 +424,7 @@ wigner_bwd_tma_kernel(const float* __restrict__ angles, const float* __restrict_
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy tile writes -> visible to the copy engine
         named_bar_sync(1 + g, WQ_GT);
-        if (t == 0) {
+        if (t == WQ_GT - 1) {      // a lane that neither builds the trig table nor sums the angle gradients
             if (j == g)
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                              :: "l"(acc), "r"(smem_u32(tile)), "r"(TILE_BYTES) : "memory");
@@ -427,11 +432,15 @@ wigner_bwd_tma_kernel(const float* __restrict__ angles, const float* __restrict_
                 asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
                              :: "l"(acc), "r"(smem_u32(tile)), "r"(TILE_BYTES) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the engine has read the buffer: refill it
+            if (j == g)     // the initialising store must have landed before the first reduce-add is issued (bulk ops are unordered)
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            else
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the engine has read the buffer: refill it
             const int64_t jn = j + WQ_BUFS;
             if (jn < my_tiles) {
-                mbar_expect_tx(full + buf, TILE_BYTES);
-                tma_load(tile, gout + (first + jn * stride) * WQ_S * MC, TILE_BYTES, full + buf);
+                uint64_t* nbar = full + 2 * buf + int((use + 1) & 1);
+                mbar_expect_tx(nbar, TILE_BYTES);
+                tma_load(tile, gout + (first + jn * stride) * WQ_S * MC, TILE_BYTES, nbar);
             }
         }
         for (int q = t; q < WQ_S * 3; q += WQ_GT) {
@@ -442,7 +451,7 @@ wigner_bwd_tma_kernel(const float* __restrict__ angles, const float* __restrict_
             gangles[n0 * 3 + q] = sum;
         }
     }
-    if (t == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all bulk reductions done before the grid retires
+    if (t == WQ_GT - 1) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all bulk reductions done before the grid retires
 }
 
 // rows [r0, r0 + chunk) of partial [nrows][MC] -> out[blockIdx.y][MC]   (first pass of the row reduction)
@@ -587,7 +596,7 @@ static int launch_bwd_tma(const WgGeom& g, const float* angles, const float* spe
     }
     const int64_t ntiles = N / WQ_S, n_full = ntiles * WQ_S, n_tail = N - n_full;
     const int grid = int(ntiles < g.sms ? ntiles : g.sms);
-    const size_t smem = size_t(WQ_BUFS * WQ_S * MC + WQ_GROUPS * WQ_S * WG_TRIG_STRIDE + WQ_GROUPS * WQ_GT * 3) * 4 + WQ_BUFS * 8;
+    const size_t smem = size_t(WQ_BUFS * WQ_S * MC + WQ_GROUPS * WQ_S * WG_TRIG_STRIDE + WQ_GROUPS * WQ_GT * 3) * 4 + 2 * WQ_BUFS * 8;
     int rc = opt_in_smem(wigner_bwd_tma_kernel<C, LT>, smem);
     if (rc) return rc;
     wigner_bwd_tma_kernel<C, LT><<<grid, WQ_THREADS, smem, st>>>(angles, spectrum, gout, gangles, workspace, ntiles, transpose);

@@ -326,3 +326,26 @@ def test_tma_backward_matches_cp_async_backward(mods, L, N, tr):
         (O.action_net_forward(a64, it64, L, tr) * g_aligned.double().cpu().view(N, -1)).sum().backward()
         close(gi1, it64.grad, 1e-5, 1e-5 * max(1.0, scale))
         close(ga1, a64.grad, 2e-5, 1e-4)
+
+
+def test_tma_backward_stress_reproducible(mods):
+    """Many back-to-back launches of the TMA-fed backward (persistent CTAs, 4 mbarrier-tracked tile buffers per SM):
+    every launch must reproduce the first one bit for bit.  Guards the buffer hand-over protocol (a single barrier per
+    buffer aliased its 1-bit phase when one math group was starved; that showed up as a rare launch failure)."""
+    from lie_vae_b200 import _ops
+    torch.manual_seed(5)
+    N, L, C = 1 << 17, 8, 10
+    M = (L + 1) ** 2
+    ang = (torch.rand(N, 3, device="cuda") * 6.0 - 3.0)
+    item = torch.randn(M, C, device="cuda")
+    g = torch.randn(N, M, C, device="cuda")
+
+    def run():
+        a, it = ang.clone().requires_grad_(True), item.clone().requires_grad_(True)
+        _ops.WignerApply.apply(a, it, 0, L, False).backward(g)
+        return a.grad, it.grad
+    ga0, gi0 = run()
+    for _ in range(300):
+        ga, gi = run()
+        assert torch.equal(gi, gi0) and torch.equal(ga, ga0)
+    torch.cuda.synchronize()
