@@ -16,8 +16,11 @@
 //   forward : columns are assembled in shared memory and the whole tile leaves with ONE TMA bulk
 //             store (cp.async.bulk.global.shared::cta) issued by one thread -- no per-thread
 //             copy-out loop, the LSU and the issue slots stay with the math;
-//   backward: the upstream-gradient tile lands by cp.async (all pieces in flight at once), the
-//             spectrum gradient overwrites it in place.
+//   backward: (shared spectrum, the ActionNet case) one persistent CTA per SM, three math groups, four
+//             tile buffers fed by TMA bulk loads on mbarriers; finished tiles are summed over the batch by
+//             TMA bulk reduce-adds into fp32 accumulators in global memory -- see wigner_bwd_tma_kernel.
+//             (per-sample spectrum, other C / degree ranges, ragged tails: wigner_bwd_kernel, where the
+//             tile lands by cp.async and the spectrum gradient overwrites it in place.)
 // Specialisations: the channel count (10, the ActionNet default) and the degree range (0..8 and
 // 0..6) are template parameters for the common cases, so the degree loop is fully unrolled and every
 // tile / spectrum access is base + immediate; <CT = 0, LT = -1> is the run-time fallback for
@@ -29,8 +32,9 @@
 //      g_a = <h4, G w4>,  g_b = <h2, G w2>,  g_c = <g_s, G s>,   w2 = J X(c) s, w4 = J X(b) w2
 // so only w2 and w4 are recomputed from the spectrum; nothing is saved by the forward.
 // For a shared spectrum (ActionNet.item_rep, decoders.py:53) the per-sample g_s are summed over
-// the batch deterministically: rows of the tile -> per-CTA accumulator in smem (persistent CTAs,
-// exactly one resident wave) -> one partial per CTA -> a second tiny kernel.  No atomics anywhere.
+// the batch reproducibly: every accumulator element receives its per-tile contributions in tile
+// order (TMA kernel: one bulk reduce-add per tile and group; cp.async kernel: per-CTA smem
+// accumulator), then one partial row per group / CTA -> a second tiny kernel.  No SM-side atomics.
 //
 // transpose=True (lie_tools.py:249-250): D^T = X(-c) J X(-b) J X(-a), i.e. the same kernels on
 // the angles (-c, -b, -a), with the angle gradients mapped back.
@@ -358,7 +362,8 @@ __device__ __forceinline__ void tma_load(void* smem_dst, const void* gsrc, uint3
 template <int CT, int LT>
 __global__ void __launch_bounds__(WQ_THREADS, 1)
 wigner_bwd_tma_kernel(const float* __restrict__ angles, const float* __restrict__ spectrum, const float* __restrict__ gout,
-                      float* __restrict__ gangles, float* __restrict__ gacc, int64_t ntiles, int transpose) {
+                      float* __restrict__ gangles, float* __restrict__ gacc, float* __restrict__ partial, int64_t ntiles,
+                      int transpose) {
     constexpr int C = CT, M = (LT + 1) * (LT + 1), MC = M * C;
     constexpr uint32_t TILE_BYTES = WQ_S * MC * 4u;
     extern __shared__ __align__(16) float smem[];
@@ -388,8 +393,6 @@ wigner_bwd_tma_kernel(const float* __restrict__ angles, const float* __restrict_
             tma_load(tiles + j * WQ_S * MC, gout + (first + j * stride) * WQ_S * MC, TILE_BYTES, full + 2 * j);
         }
     }
-    if (g >= my_tiles)      // a group without work still owns an accumulator that the final reduction reads
-        for (int o = t; o < WQ_S * MC; o += WQ_GT) acc[o] = 0.f;
     for (int64_t j = g; j < my_tiles; j += WQ_GROUPS) {
         const int buf = int(j % WQ_BUFS);
         const int64_t use = j / WQ_BUFS;                       // how often this buffer has been filled before
@@ -451,25 +454,25 @@ wigner_bwd_tma_kernel(const float* __restrict__ angles, const float* __restrict_
             gangles[n0 * 3 + q] = sum;
         }
     }
-    if (t == WQ_GT - 1) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all bulk reductions done before the grid retires
-}
-
-// rows [r0, r0 + chunk) of partial [nrows][MC] -> out[blockIdx.y][MC]   (first pass of the row reduction)
-__global__ void __launch_bounds__(256)
-wigner_reduce_chunks(const float* __restrict__ partial, float* __restrict__ out, int nrows, int chunk, int MC) {
-    __shared__ float red[8][33];
-    const int o = blockIdx.x * 32 + threadIdx.x;
-    const int r0 = blockIdx.y * chunk, r1 = min(nrows, r0 + chunk);
-    float acc = 0.f;
-    if (o < MC)
-        for (int b = r0 + threadIdx.y; b < r1; b += 8) acc += partial[int64_t(b) * MC + o];
-    red[threadIdx.y][threadIdx.x] = acc;
-    __syncthreads();
-    if (threadIdx.y == 0 && o < MC) {
-        float a = 0.f;
+    // The group's 16-row accumulator -> one partial row.  The issuing lane waits until all of its bulk reductions have
+    // been performed, orders the async-proxy writes before the generic-proxy reads below, and the group barrier hands
+    // that ordering to the other lanes; the reads bypass L1 (the SM never cached these lines).
+    if (t == WQ_GT - 1) {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");
+        __threadfence();
+    }
+    named_bar_sync(1 + g, WQ_GT);
+    float* prow = partial + (int64_t(blockIdx.x) * WQ_GROUPS + g) * MC;
+    if (g < my_tiles) {
+        for (int o = t; o < MC; o += WQ_GT) {
+            float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-        for (int y = 0; y < 8; ++y) a += red[y][threadIdx.x];
-        out[int64_t(blockIdx.y) * MC + o] = a;
+            for (int r = 0; r < WQ_S; r += 2) { a0 += __ldcg(acc + r * MC + o); a1 += __ldcg(acc + (r + 1) * MC + o); }
+            prow[o] = a0 + a1;
+        }
+    } else {
+        for (int o = t; o < MC; o += WQ_GT) prow[o] = 0.f;      // a group without work contributes a zero row
     }
 }
 
@@ -575,16 +578,12 @@ static int launch_bwd(const WgGeom& g, const float* angles, const float* spectru
 }
 
 // ---- TMA-fed backward (shared spectrum, C = 10, degrees 0..8 or 0..6, 16-byte aligned g_y) -------------------------
-constexpr int WQ_CHUNK = 128;      // rows per block in the first pass of the final row reduction
 
 static bool tma_bwd_eligible(int C, int lmin, int lmax, const float* gout, int64_t N) {
     return C == 10 && lmin == 0 && (lmax == 8 || lmax == 6) && N >= WQ_S && (reinterpret_cast<uintptr_t>(gout) & 15u) == 0;
 }
-// workspace rows (of MC floats): accumulators [sms*3*16] | tail partial [1] | chunk sums [ceil(rows / WQ_CHUNK)]
-static int64_t tma_bwd_workspace_rows(int sms) {
-    const int64_t rows = int64_t(sms) * WQ_GROUPS * WQ_S + 1;
-    return rows + (rows + WQ_CHUNK - 1) / WQ_CHUNK;
-}
+// workspace rows (of MC floats): accumulators [sms*3*16] | one partial row per (CTA, group) [sms*3] | tail partial [1]
+static int64_t tma_bwd_workspace_rows(int sms) { return int64_t(sms) * WQ_GROUPS * (WQ_S + 1) + 1; }
 
 template <int LT>
 static int launch_bwd_tma(const WgGeom& g, const float* angles, const float* spectrum, const float* gout, float* gangles,
@@ -599,24 +598,21 @@ static int launch_bwd_tma(const WgGeom& g, const float* angles, const float* spe
     const size_t smem = size_t(WQ_BUFS * WQ_S * MC + WQ_GROUPS * WQ_S * WG_TRIG_STRIDE + WQ_GROUPS * WQ_GT * 3) * 4 + 2 * WQ_BUFS * 8;
     int rc = opt_in_smem(wigner_bwd_tma_kernel<C, LT>, smem);
     if (rc) return rc;
-    wigner_bwd_tma_kernel<C, LT><<<grid, WQ_THREADS, smem, st>>>(angles, spectrum, gout, gangles, workspace, ntiles, transpose);
+    float* partial = workspace + int64_t(g.sms) * WQ_GROUPS * WQ_S * MC;
+    wigner_bwd_tma_kernel<C, LT><<<grid, WQ_THREADS, smem, st>>>(angles, spectrum, gout, gangles, workspace, partial, ntiles, transpose);
     if ((rc = check_launch("wigner_apply_bwd (tma)"))) return rc;
-    int rows = grid * WQ_GROUPS * WQ_S;
+    int rows = grid * WQ_GROUPS;
     if (n_tail > 0) {
-        // ragged tail (< 16 samples): the cp.async kernel, one CTA, its partial row goes right after the accumulators
+        // ragged tail (< 16 samples): the cp.async kernel, one CTA, its partial row goes right after the others
         WgGeom gt = g;
         gt.ntiles = (n_tail + g.S - 1) / g.S;
         int tail_grid = 0;
         rc = launch_bwd<true, 0, -1>(gt, angles + n_full * 3, spectrum, gout + n_full * MC, gangles + n_full * 3, nullptr,
-                                     workspace + int64_t(rows) * MC, int64_t(gt.ntiles) * MC, n_tail, 0, LT, C, transpose, st, &tail_grid);
+                                     partial + int64_t(rows) * MC, int64_t(gt.ntiles) * MC, n_tail, 0, LT, C, transpose, st, &tail_grid);
         if (rc) return rc;
         rows += tail_grid;
     }
-    const int nchunks = (rows + WQ_CHUNK - 1) / WQ_CHUNK;
-    float* chunk_sums = workspace + int64_t(rows) * MC;
-    wigner_reduce_chunks<<<dim3((MC + 31) / 32, nchunks), dim3(32, 8), 0, st>>>(workspace, chunk_sums, rows, WQ_CHUNK, MC);
-    if ((rc = check_launch("wigner_reduce_chunks"))) return rc;
-    wigner_reduce_partials<<<(MC + 31) / 32, dim3(32, 8), 0, st>>>(chunk_sums, gspectrum, nchunks, MC);
+    wigner_reduce_partials<<<(MC + 31) / 32, dim3(32, 8), 0, st>>>(partial, gspectrum, rows, MC);
     return check_launch("wigner_reduce_partials");
 }
 

@@ -46,7 +46,7 @@ class FusedSO3ActionStep:
     resident for the full shard.
     """
 
-    LAUNCHES_PER_MICROBATCH = 4      # wigner fwd, wigner bwd (TMA-fed), wigner_reduce_chunks, wigner_reduce_partials
+    LAUNCHES_PER_MICROBATCH = 3      # wigner fwd, wigner bwd (TMA-fed), wigner_reduce_partials
     LAUNCHES_PER_SHARD = 4           # reparam fwd, eazyz fwd, eazyz bwd, reparam bwd
 
     def __init__(self, shard, micro, degrees=8, rep_copies=10, k=3, transpose=False, device="cuda"):
