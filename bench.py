@@ -36,6 +36,7 @@ TOTAL_SAMPLES = 1 << 24
 MICRO = 1 << 18
 L_MAX, CHANNELS, K_WIND = 8, 10, 3
 FALLBACK_HBM_GBS = 6650.0
+CPU_SAMPLE = 1 << 16        # bounded CPU sample (= BASELINE config 3's batch); a few seconds per step on 16 cores
 
 
 def measured_peaks():
@@ -133,7 +134,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = 1 << 14
+    sample = CPU_SAMPLE
     times = cpu_reference_run(sample, args.steps, max(1, min(args.warmup, 2)), threads)
     ms = 1e3 * sum(times) / len(times)
     value = sample / (ms / 1e3)
@@ -277,8 +278,8 @@ def run_ours(args):
             main.wait_event(ready[b])
             m = stage[b][0].requires_grad_(True)
             s = stage[b][1].requires_grad_(True)
-            z, lq = rp.so3_reparameterize(m, s, stage[b][2], K_WIND)
-            ang = lt.group_matrix_to_eazyz(z[0])
+            ang3, lq = rp.so3_reparameterize_eazyz(m, s, stage[b][2], K_WIND)
+            ang = ang3[0]
             yy = _ops.WignerApply.apply(ang, item_p, 0, L_MAX, False)
             # the decoder that would consume y is outside the hot path: its gradient g_y (and g_log_q) is handed
             # to autograd directly, exactly as a downstream module's backward would
@@ -331,7 +332,6 @@ def run_ours(args):
             kernels[k] = {"avg_ms": round(avg_ms, 4), "samples_per_launch": per_launch, "bytes_per_sample": abytes[k],
                           "gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
         dom = "wigner_bwd"
-        fused_bytes = sum(abytes.values()) - (36 + 36) - (12 + 12) - (12 + 12) - (36 + 36)   # minus z, angles, g_angles, g_z round trips
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -340,7 +340,7 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": samples_per_step / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": n_loc * 60, "d2h_bytes_per_step": 4 * (1 + M * CHANNELS),
-                    "api": "so3_reparameterize -> group_matrix_to_eazyz -> WignerApply (autograd), pinned host mu/sigma/eps, double-buffered copies"},
+                    "api": "so3_reparameterize_eazyz -> WignerApply (torch.autograd), pinned host mu/sigma/eps, double-buffered copies"},
             "gpu_launches": (step_obj.LAUNCHES_PER_MICROBATCH * n_micro + step_obj.LAUNCHES_PER_SHARD) * args.steps,
             "roofline": {"bound": "hbm", "kernel": "wigner_bwd_tma_kernel<10,8> (+ row-reduction kernels)", "achieved": kernels[dom]["gbs"], "peak": peak,
                          "unit": "GB/s", "frac": kernels[dom]["frac"],
@@ -355,7 +355,7 @@ def run_ours(args):
         }
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
-            sample = 1 << 14
+            sample = CPU_SAMPLE
             times = cpu_reference_run(sample, 3, 1, threads)
             best = min(times)
             line["cpu_baseline"] = {"value": sample / best, "unit": UNIT, "cores": threads, "kind": "port",

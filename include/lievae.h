@@ -109,6 +109,15 @@ int lv_so3_reparam_fwd_f32(const float* mu, const float* sigma, const float* eps
 int lv_so3_reparam_bwd_f32(const float* mu, const float* sigma, const float* eps, const float* gz, const float* glq,
                            float* gmu, float* gsigma, int64_t n, int64_t B, int k, void* stream);
 
+/* ---- the same, fused with group_matrix_to_eazyz (lie_tools.py:178-180, the pose handed to the action decoder in
+ *   VAE.decode, experiments/vae.py:182): angles (n,B,3) = ZYZ Euler angles of z.  z may be NULL (not stored).
+ *   Backward: gangles (n,B,3) required; gz, glq may be NULL (=0). ---- */
+int lv_so3_reparam_eazyz_fwd_f32(const float* mu, const float* sigma, const float* eps, float* z, float* angles,
+                                 float* log_q, int64_t n, int64_t B, int k, void* stream);
+int lv_so3_reparam_eazyz_bwd_f32(const float* mu, const float* sigma, const float* eps, const float* gz,
+                                 const float* gangles, const float* glq, float* gmu, float* gsigma, int64_t n, int64_t B,
+                                 int k, void* stream);
+
 /* ---- block-diagonal Wigner-D action on a spectrum, degrees lmin..lmax (<= 8), C channels.
  *   block_wigner_matrix_multiply lie_tools.py:226-253, wigner_d_matrix lie_tools.py:211-223,
  *   _z_rot_mat lie_tools.py:195-208, ActionNet.forward decoders.py:47-56.

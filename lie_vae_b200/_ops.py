@@ -168,6 +168,53 @@ class SO3Reparam(Function):
         return sum_leading(gmu), sum_leading(gsg), None, None
 
 
+class SO3ReparamEazyz(Function):
+    """(mu, sigma, eps, k) -> angles (n,B,3), log_q (n,B): reparameterize fused with matrix -> ZYZ Euler.
+
+    The pose z = mu @ exp(hat(eps*sigma)) stays in registers; only its Euler angles (what VAE.decode hands
+    to the action decoder, ``experiments/vae.py:182``) and the log-density are written.   float32.
+    """
+
+    @staticmethod
+    def forward(ctx, mu, sigma, eps, k):
+        dev = _require_cuda(mu, sigma, eps)
+        for t in (mu, sigma, eps):
+            if t.dtype != torch.float32:
+                raise TypeError("so3_reparameterize_eazyz is float32 only, got %s" % t.dtype)
+        if mu.dim() != 3 or tuple(mu.shape[1:]) != (3, 3):
+            raise ValueError("mu must be (B,3,3), got %s" % (tuple(mu.shape),))
+        B = mu.shape[0]
+        if tuple(sigma.shape) != (B, 3):
+            raise ValueError("sigma must be (B,3), got %s" % (tuple(sigma.shape),))
+        if eps.dim() != 3 or tuple(eps.shape[1:]) != (B, 3):
+            raise ValueError("eps must be (n,B,3), got %s" % (tuple(eps.shape),))
+        n = eps.shape[0]
+        mu_c, sg_c, ep_c = mu.contiguous(), sigma.contiguous(), eps.contiguous()
+        angles = torch.empty((n, B, 3), dtype=torch.float32, device=dev)
+        log_q = torch.empty((n, B), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _cabi.call("lv_so3_reparam_eazyz_fwd_f32", _cabi.ptr(mu_c), _cabi.ptr(sg_c), _cabi.ptr(ep_c), None,
+                       _cabi.ptr(angles), _cabi.ptr(log_q), n, B, int(k), _stream())
+        ctx.save_for_backward(mu_c, sg_c, ep_c)
+        ctx.k = int(k)
+        return angles, log_q
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gang, glq):
+        mu, sigma, eps = ctx.saved_tensors
+        n, B = eps.shape[0], eps.shape[1]
+        dev = mu.device
+        gang = torch.zeros((n, B, 3), dtype=torch.float32, device=dev) if gang is None else gang.contiguous()
+        glq = None if glq is None else glq.contiguous()
+        gmu = torch.empty((n, B, 3, 3), dtype=torch.float32, device=dev)
+        gsg = torch.empty((n, B, 3), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _cabi.call("lv_so3_reparam_eazyz_bwd_f32", _cabi.ptr(mu), _cabi.ptr(sigma), _cabi.ptr(eps), None, _cabi.ptr(gang),
+                       _cabi.ptr(glq), _cabi.ptr(gmu), _cabi.ptr(gsg), n, B, ctx.k, _stream())
+        return sum_leading(gmu), sum_leading(gsg), None, None
+
+
 # ------------------------------------------------------------------------------ Wigner-D action
 class WignerApply(Function):
     """angles (N,3), spectrum ((M,C) shared | (N,M,C)) -> (N,M,C), degrees lmin..lmax.   float32."""

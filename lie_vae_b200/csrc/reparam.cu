@@ -134,13 +134,16 @@ __device__ __forceinline__ void stage_bcast(float* __restrict__ dst, const float
 }
 
 // ------------------------------------------------------------------ forward
-template <int KT>
+// EULER: additionally emit the ZYZ Euler angles of z (group_matrix_to_eazyz, lie_tools.py:178-180 -- what
+// VAE.decode feeds the action decoder, vae.py:182) from the registers that hold z; z itself is then optional.
+template <int KT, bool EULER>
 __global__ void __launch_bounds__(RP_TILE)
 so3_reparam_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ sigma, const float* __restrict__ eps,
-                       float* __restrict__ z, float* __restrict__ log_q, int64_t total, int64_t B, int krt) {
+                       float* __restrict__ z, float* __restrict__ angles, float* __restrict__ log_q, int64_t total,
+                       int64_t B, int krt) {
     __shared__ __align__(16) float s_m[RP_TILE * 9];   // mu in, z out (same row, same thread)
     __shared__ __align__(16) float s_s[RP_TILE * 3];
-    __shared__ __align__(16) float s_e[RP_TILE * 3];
+    __shared__ __align__(16) float s_e[RP_TILE * 3];   // eps in, Euler angles out
     const int64_t i0 = int64_t(blockIdx.x) * RP_TILE;
     const int rows = int(min(int64_t(RP_TILE), total - i0));
     stage_bcast<9>(s_m, mu, i0, rows, B);
@@ -157,13 +160,22 @@ so3_reparam_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ s
         for (int j = 0; j < 3; ++j) { sg[j] = s_s[t * 3 + j]; v[j] = s_e[t * 3 + j] * sg[j]; }
         RodriguesCtx<float> k;
         rodrigues_ctx(v, k);
-        float R[9];
+        float R[9], zr[9];
         axis_angle_matrix(k.u, k.s, k.w, R);
 #pragma unroll
         for (int r = 0; r < 3; ++r)
 #pragma unroll
-            for (int c = 0; c < 3; ++c)
-                s_m[t * 9 + r * 3 + c] = fmaf(m[r * 3], R[c], fmaf(m[r * 3 + 1], R[3 + c], m[r * 3 + 2] * R[6 + c]));
+            for (int c = 0; c < 3; ++c) {
+                zr[r * 3 + c] = fmaf(m[r * 3], R[c], fmaf(m[r * 3 + 1], R[3 + c], m[r * 3 + 2] * R[6 + c]));
+                s_m[t * 9 + r * 3 + c] = zr[r * 3 + c];
+            }
+        if (EULER) {
+            float q[4], e[3];
+            mat_to_quat_fwd(zr, q);
+            quat_to_eazyz_fwd(q, e);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) s_e[t * 3 + j] = e[j];
+        }
         if (log_q != nullptr) {
             const float q0 = k.u[0] / sg[0], q1 = k.u[1] / sg[1], q2 = k.u[2] / sg[2];
             const float a = 0.5f * (q0 * q0 + q1 * q1 + q2 * q2);
@@ -173,27 +185,31 @@ so3_reparam_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ s
         }
     }
     __syncthreads();
-    tile_s2g(z + i0 * 9, s_m, rows * 9);
+    if (z != nullptr) tile_s2g(z + i0 * 9, s_m, rows * 9);
+    if (EULER) tile_s2g(angles + i0 * 3, s_e, rows * 3);
 }
 
 // ------------------------------------------------------------------ backward
 // per-sample gradients: g_mu (total,9), g_sigma (total,3); for n > 1 the caller sums over n
-// (lv_sum_leading_f32).
-template <int KT>
+// (lv_sum_leading_f32).  EULER: the upstream gradient arrives (also) as g_angles and is pulled back
+// through matrix -> quaternion -> Euler on the recomputed z.
+template <int KT, bool EULER>
 __global__ void __launch_bounds__(RP_TILE)
 so3_reparam_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ sigma, const float* __restrict__ eps,
-                       const float* __restrict__ gz, const float* __restrict__ glq,
+                       const float* __restrict__ gz, const float* __restrict__ gangles, const float* __restrict__ glq,
                        float* __restrict__ gmu, float* __restrict__ gsigma, int64_t total, int64_t B, int krt) {
     __shared__ __align__(16) float s_m[RP_TILE * 9];
     __shared__ __align__(16) float s_g[RP_TILE * 9];   // gz in, g_mu out
     __shared__ __align__(16) float s_s[RP_TILE * 3];
     __shared__ __align__(16) float s_e[RP_TILE * 3];   // eps in, g_sigma out
+    __shared__ __align__(16) float s_a[EULER ? RP_TILE * 3 : 4];   // g_angles in
     const int64_t i0 = int64_t(blockIdx.x) * RP_TILE;
     const int rows = int(min(int64_t(RP_TILE), total - i0));
     stage_bcast<9>(s_m, mu, i0, rows, B);
     stage_bcast<3>(s_s, sigma, i0, rows, B);
     tile_g2s(s_e, eps + i0 * 3, rows * 3);
     if (gz != nullptr) tile_g2s(s_g, gz + i0 * 9, rows * 9);
+    if (EULER) tile_g2s(s_a, gangles + i0 * 3, rows * 3);
     tile_async_wait();
     __syncthreads();
     const int t = threadIdx.x;
@@ -207,6 +223,21 @@ so3_reparam_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ s
         rodrigues_ctx(v, k);
         float R[9];
         axis_angle_matrix(k.u, k.s, k.w, R);
+        if (EULER) {
+            float zr[9], q[4], ge[3], gq[4], gze[9];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    zr[r * 3 + c] = fmaf(m[r * 3], R[c], fmaf(m[r * 3 + 1], R[3 + c], m[r * 3 + 2] * R[6 + c]));
+#pragma unroll
+            for (int j = 0; j < 3; ++j) ge[j] = s_a[t * 3 + j];
+            mat_to_quat_fwd(zr, q);
+            quat_to_eazyz_bwd(q, ge, gq);
+            mat_to_quat_bwd(zr, gq, gze);
+#pragma unroll
+            for (int j = 0; j < 9; ++j) G[j] += gze[j];
+        }
         // z = mu R:  g_mu = gz R^T,  g_R = mu^T gz
         float gR[9];
 #pragma unroll
@@ -257,33 +288,58 @@ static int reparam_check(const char* name, int64_t n, int64_t B, int k) {
     return LV_OK;
 }
 
-extern "C" int lv_so3_reparam_fwd_f32(const float* mu, const float* sigma, const float* eps, float* z, float* log_q,
-                                      int64_t n, int64_t B, int k, void* stream) {
-    int rc = reparam_check("so3_reparam_fwd", n, B, k);
+template <bool EULER>
+static int reparam_fwd(const char* name, const float* mu, const float* sigma, const float* eps, float* z, float* angles,
+                       float* log_q, int64_t n, int64_t B, int k, void* stream) {
+    int rc = reparam_check(name, n, B, k);
     if (rc) return rc;
     const int64_t total = n * B;
     if (total == 0) return LV_OK;
-    if (!mu || !sigma || !eps || !z) { lv::set_error("so3_reparam_fwd: null pointer"); return LV_ERR_ARG; }
+    if (!mu || !sigma || !eps || (EULER ? !angles : !z)) { lv::set_error("%s: null pointer", name); return LV_ERR_ARG; }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const unsigned grid = unsigned((total + lv::RP_TILE - 1) / lv::RP_TILE);
-    if (k == 3) lv::so3_reparam_fwd_kernel<3><<<grid, lv::RP_TILE, 0, st>>>(mu, sigma, eps, z, log_q, total, B, k);
-    else if (k == 10) lv::so3_reparam_fwd_kernel<10><<<grid, lv::RP_TILE, 0, st>>>(mu, sigma, eps, z, log_q, total, B, k);
-    else lv::so3_reparam_fwd_kernel<0><<<grid, lv::RP_TILE, 0, st>>>(mu, sigma, eps, z, log_q, total, B, k);
-    return lv::check_launch("so3_reparam_fwd");
+    if (k == 3) lv::so3_reparam_fwd_kernel<3, EULER><<<grid, lv::RP_TILE, 0, st>>>(mu, sigma, eps, z, angles, log_q, total, B, k);
+    else if (k == 10) lv::so3_reparam_fwd_kernel<10, EULER><<<grid, lv::RP_TILE, 0, st>>>(mu, sigma, eps, z, angles, log_q, total, B, k);
+    else lv::so3_reparam_fwd_kernel<0, EULER><<<grid, lv::RP_TILE, 0, st>>>(mu, sigma, eps, z, angles, log_q, total, B, k);
+    return lv::check_launch(name);
+}
+
+template <bool EULER>
+static int reparam_bwd(const char* name, const float* mu, const float* sigma, const float* eps, const float* gz,
+                       const float* gangles, const float* glq, float* gmu, float* gsigma, int64_t n, int64_t B, int k,
+                       void* stream) {
+    int rc = reparam_check(name, n, B, k);
+    if (rc) return rc;
+    const int64_t total = n * B;
+    if (total == 0) return LV_OK;
+    if (!mu || !sigma || !eps || !gmu || !gsigma || (EULER && !gangles)) { lv::set_error("%s: null pointer", name); return LV_ERR_ARG; }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const unsigned grid = unsigned((total + lv::RP_TILE - 1) / lv::RP_TILE);
+    if (k == 3) lv::so3_reparam_bwd_kernel<3, EULER><<<grid, lv::RP_TILE, 0, st>>>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, total, B, k);
+    else if (k == 10) lv::so3_reparam_bwd_kernel<10, EULER><<<grid, lv::RP_TILE, 0, st>>>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, total, B, k);
+    else lv::so3_reparam_bwd_kernel<0, EULER><<<grid, lv::RP_TILE, 0, st>>>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, total, B, k);
+    return lv::check_launch(name);
+}
+
+extern "C" int lv_so3_reparam_fwd_f32(const float* mu, const float* sigma, const float* eps, float* z, float* log_q,
+                                      int64_t n, int64_t B, int k, void* stream) {
+    return reparam_fwd<false>("so3_reparam_fwd", mu, sigma, eps, z, nullptr, log_q, n, B, k, stream);
 }
 
 extern "C" int lv_so3_reparam_bwd_f32(const float* mu, const float* sigma, const float* eps, const float* gz,
                                       const float* glq, float* gmu, float* gsigma, int64_t n, int64_t B, int k,
                                       void* stream) {
-    int rc = reparam_check("so3_reparam_bwd", n, B, k);
-    if (rc) return rc;
-    const int64_t total = n * B;
-    if (total == 0) return LV_OK;
-    if (!mu || !sigma || !eps || !gmu || !gsigma) { lv::set_error("so3_reparam_bwd: null pointer"); return LV_ERR_ARG; }
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const unsigned grid = unsigned((total + lv::RP_TILE - 1) / lv::RP_TILE);
-    if (k == 3) lv::so3_reparam_bwd_kernel<3><<<grid, lv::RP_TILE, 0, st>>>(mu, sigma, eps, gz, glq, gmu, gsigma, total, B, k);
-    else if (k == 10) lv::so3_reparam_bwd_kernel<10><<<grid, lv::RP_TILE, 0, st>>>(mu, sigma, eps, gz, glq, gmu, gsigma, total, B, k);
-    else lv::so3_reparam_bwd_kernel<0><<<grid, lv::RP_TILE, 0, st>>>(mu, sigma, eps, gz, glq, gmu, gsigma, total, B, k);
-    return lv::check_launch("so3_reparam_bwd");
+    return reparam_bwd<false>("so3_reparam_bwd", mu, sigma, eps, gz, nullptr, glq, gmu, gsigma, n, B, k, stream);
+}
+
+// reparameterize fused with matrix -> ZYZ Euler (the pose the action decoder consumes); z is optional
+extern "C" int lv_so3_reparam_eazyz_fwd_f32(const float* mu, const float* sigma, const float* eps, float* z, float* angles,
+                                            float* log_q, int64_t n, int64_t B, int k, void* stream) {
+    return reparam_fwd<true>("so3_reparam_eazyz_fwd", mu, sigma, eps, z, angles, log_q, n, B, k, stream);
+}
+
+extern "C" int lv_so3_reparam_eazyz_bwd_f32(const float* mu, const float* sigma, const float* eps, const float* gz,
+                                            const float* gangles, const float* glq, float* gmu, float* gsigma, int64_t n,
+                                            int64_t B, int k, void* stream) {
+    return reparam_bwd<true>("so3_reparam_eazyz_bwd", mu, sigma, eps, gz, gangles, glq, gmu, gsigma, n, B, k, stream);
 }

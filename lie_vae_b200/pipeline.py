@@ -1,39 +1,37 @@
 """Pre-allocated, graph-free runner of the fused hot path (host-side plumbing).
 
-One *micro-batch step* is what ``VAE.elbo`` + ``backward`` spend in the SO(3)
-latent modules of the reference (``experiments/vae.py:134-190``):
+One *step* is what ``VAE.elbo`` + ``backward`` spend in the SO(3) latent modules of the reference
+(``experiments/vae.py:134-190``), as four kernels:
 
-    reparameterize fwd   (mu, sigma, eps)     -> z, log_q        reparameterize.py:220-263
-    matrix -> ZYZ Euler   z                   -> angles          vae.py:182, lie_tools.py:178
-    Wigner action fwd     angles, item_rep    -> y               decoders.py:47-56
-    Wigner action bwd     g_y                 -> g_angles, g_item_rep
-    Euler bwd             g_angles            -> g_z
-    reparameterize bwd    g_z, g_log_q        -> g_mu, g_sigma
+    latent fwd    (mu, sigma, eps)          -> angles, log_q     reparameterize.py:220-263 + vae.py:182 / lie_tools.py:178
+    Wigner fwd    angles, item_rep          -> y                 decoders.py:47-56
+    Wigner bwd    g_y                       -> g_angles, g_item_rep
+    latent bwd    g_angles, g_log_q         -> g_mu, g_sigma
 
-It calls the C ABI directly on caller-owned buffers (no autograd graph, no
-allocation in the loop), which is how ``bench.py`` times the kernels with
-inputs resident in HBM, and how a training loop that owns its buffers would
-drive them.  The autograd modules in ``reparameterize.py`` / ``decoders.py``
-are the drop-in API; this class is the same kernels without the tape.
+The latent kernels are the reparameterize kernels fused with matrix -> ZYZ Euler: the sampled pose z never
+touches HBM (the backward recomputes it from mu, sigma, eps).  This class calls the C ABI directly on
+caller-owned buffers (no autograd graph, no allocation in the loop), which is how ``bench.py`` times the
+kernels with inputs resident in HBM, and how a training loop that owns its buffers would drive them.  The
+autograd modules in ``reparameterize.py`` / ``decoders.py`` are the drop-in API; this is the same kernels
+without the tape.
 """
 import torch
 
 from . import _cabi
 from ._ops import _stream
 
-KERNELS = ("reparam_fwd", "eazyz_fwd", "wigner_fwd", "wigner_bwd", "eazyz_bwd", "reparam_bwd")
+KERNELS = ("latent_fwd", "wigner_fwd", "wigner_bwd", "latent_bwd")
 
-# algorithmic HBM bytes per sample of each launch (FP32; SURVEY.md 8d, DESIGN.md "Roofline")
+
 def algorithmic_bytes(L, C):
+    """Algorithmic HBM bytes per sample of each launch (FP32)."""
     M = (L + 1) ** 2
     y = 4 * M * C
     return {
-        "reparam_fwd": 36 + 12 + 12 + 36 + 4,          # mu, sigma, eps -> z, log_q
-        "eazyz_fwd": 36 + 12,                          # z -> angles
-        "wigner_fwd": 12 + y,                          # angles -> y   (item_rep is per step, not per sample)
-        "wigner_bwd": y + 12 + 12,                     # g_y, angles -> g_angles
-        "eazyz_bwd": 36 + 12 + 36,                     # z, g_angles -> g_z
-        "reparam_bwd": 36 + 12 + 12 + 36 + 4 + 36 + 12,  # mu, sigma, eps, g_z, g_lq -> g_mu, g_sigma
+        "latent_fwd": 36 + 12 + 12 + 12 + 4,            # mu, sigma, eps -> angles, log_q
+        "wigner_fwd": 12 + y,                           # angles -> y   (item_rep is per step, not per sample)
+        "wigner_bwd": y + 12 + 12,                      # g_y, angles -> g_angles
+        "latent_bwd": 36 + 12 + 12 + 12 + 4 + 36 + 12,  # mu, sigma, eps, g_angles, g_lq -> g_mu, g_sigma
     }
 
 
@@ -41,13 +39,12 @@ class FusedSO3ActionStep:
     """Buffers + launches for a shard of ``shard`` samples (n = 1 sample per datapoint), decoded in
     micro-batches of ``micro`` samples.
 
-    The latent kernels (reparameterize, Euler; ~0.5 kB/sample) run once over the whole shard; only the
-    Wigner action, whose output is 3.2 kB/sample, is micro-batched so that y / g_y never need to be
-    resident for the full shard.
+    The latent kernels (~0.2 kB/sample) run once over the whole shard; only the Wigner action, whose output
+    is 3.2 kB/sample, is micro-batched so that y / g_y never need to be resident for the full shard.
     """
 
     LAUNCHES_PER_MICROBATCH = 3      # wigner fwd, wigner bwd (TMA-fed), wigner_reduce_partials
-    LAUNCHES_PER_SHARD = 4           # reparam fwd, eazyz fwd, eazyz bwd, reparam bwd
+    LAUNCHES_PER_SHARD = 2           # latent fwd, latent bwd
 
     def __init__(self, shard, micro, degrees=8, rep_copies=10, k=3, transpose=False, device="cuda"):
         self.shard, self.micro = int(shard), int(micro)
@@ -55,10 +52,8 @@ class FusedSO3ActionStep:
         self.M = (self.L + 1) ** 2
         self.device = torch.device(device)
         f32 = dict(dtype=torch.float32, device=self.device)
-        self.z = torch.empty((self.shard, 3, 3), **f32)
         self.angles = torch.empty((self.shard, 3), **f32)
         self.g_angles = torch.empty((self.shard, 3), **f32)
-        self.g_z = torch.empty((self.shard, 3, 3), **f32)
         self.g_item = torch.empty((self.M, self.C), **f32)      # gradient of the last decoded micro-batch
         with torch.cuda.device(self.device):
             nws = _cabi.lib().lv_wigner_bwd_workspace_floats(self.micro, 0, self.L, self.C)
@@ -81,25 +76,28 @@ class FusedSO3ActionStep:
         b.record()
         self.events[name].append((a, b))
 
-    def latent_forward(self, mu, sigma, eps, log_q):
-        """mu (B,3,3), sigma (B,3), eps (B,3) -> log_q (B); z and the Euler angles stay in the step's buffers."""
+    def latent_forward(self, mu, sigma, eps, log_q, z=None):
+        """mu (B,3,3), sigma (B,3), eps (B,3) -> log_q (B); the Euler angles of the sampled pose stay in the
+        step's buffer, the pose itself is written only if ``z`` (B,3,3) is given."""
         B, st, p = mu.shape[0], _stream(), _cabi.ptr
-        self._timed("reparam_fwd", lambda: _cabi.call("lv_so3_reparam_fwd_f32", p(mu), p(sigma), p(eps), p(self.z), p(log_q), 1, B, self.k, st))
-        self._timed("eazyz_fwd", lambda: _cabi.call("lv_mat_to_eazyz_fwd_f32", p(self.z), p(self.angles), B, st))
+        self._timed("latent_fwd", lambda: _cabi.call("lv_so3_reparam_eazyz_fwd_f32", p(mu), p(sigma), p(eps), p(z), p(self.angles),
+                                                    p(log_q), 1, B, self.k, st))
 
     def decode_forward(self, lo, hi, item_rep, y):
         """Wigner action of samples [lo, hi) on item_rep (M,C) -> y (hi-lo, M, C)."""
         st, p = _stream(), _cabi.ptr
-        self._timed("wigner_fwd", lambda: _cabi.call("lv_wigner_apply_fwd_f32", p(self.angles[lo:hi]), p(item_rep), p(y), hi - lo, 0, self.L, self.C, 1, int(self.transpose), st))
+        self._timed("wigner_fwd", lambda: _cabi.call("lv_wigner_apply_fwd_f32", p(self.angles[lo:hi]), p(item_rep), p(y), hi - lo, 0, self.L,
+                                                    self.C, 1, int(self.transpose), st))
 
     def decode_backward(self, lo, hi, item_rep, g_y):
         """g_y (hi-lo, M, C) -> g_angles[lo:hi] and self.g_item (M,C) for this micro-batch."""
         st, p = _stream(), _cabi.ptr
-        self._timed("wigner_bwd", lambda: _cabi.call("lv_wigner_apply_bwd_f32", p(self.angles[lo:hi]), p(item_rep), p(g_y), p(self.g_angles[lo:hi]), p(self.g_item),
-                                                    p(self.workspace), self.nws, hi - lo, 0, self.L, self.C, 1, int(self.transpose), st))
+        self._timed("wigner_bwd", lambda: _cabi.call("lv_wigner_apply_bwd_f32", p(self.angles[lo:hi]), p(item_rep), p(g_y), p(self.g_angles[lo:hi]),
+                                                    p(self.g_item), p(self.workspace), self.nws, hi - lo, 0, self.L, self.C, 1,
+                                                    int(self.transpose), st))
 
-    def latent_backward(self, mu, sigma, eps, g_log_q, g_mu, g_sigma):
-        """g_angles (from decode_backward) and g_log_q (B) -> g_mu (B,3,3), g_sigma (B,3)."""
+    def latent_backward(self, mu, sigma, eps, g_log_q, g_mu, g_sigma, g_z=None):
+        """g_angles (from decode_backward), g_log_q (B) and optionally g_z (B,3,3) -> g_mu (B,3,3), g_sigma (B,3)."""
         B, st, p = mu.shape[0], _stream(), _cabi.ptr
-        self._timed("eazyz_bwd", lambda: _cabi.call("lv_mat_to_eazyz_bwd_f32", p(self.z), p(self.g_angles), p(self.g_z), B, st))
-        self._timed("reparam_bwd", lambda: _cabi.call("lv_so3_reparam_bwd_f32", p(mu), p(sigma), p(eps), p(self.g_z), p(g_log_q), p(g_mu), p(g_sigma), 1, B, self.k, st))
+        self._timed("latent_bwd", lambda: _cabi.call("lv_so3_reparam_eazyz_bwd_f32", p(mu), p(sigma), p(eps), p(g_z), p(self.g_angles),
+                                                    p(g_log_q), p(g_mu), p(g_sigma), 1, B, self.k, st))

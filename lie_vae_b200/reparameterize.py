@@ -18,7 +18,7 @@ from . import _ops
 from .lie_tools import rodrigues, quaternions_to_group_matrix, s2s1rodrigues, s2s2_gram_schmidt
 
 __all__ = ["N0reparameterize", "AlgebraMean", "QuaternionMean", "S2S1Mean", "S2S2Mean", "SO3reparameterize",
-           "so3_reparameterize", "LOG_PRIOR_SO3"]
+           "so3_reparameterize", "so3_reparameterize_eazyz", "LOG_PRIOR_SO3"]
 
 LOG_PRIOR_SO3 = -math.log(8.0 * math.pi ** 2)   # reparameterize.py:266
 
@@ -31,6 +31,16 @@ def so3_reparameterize(mu, sigma, eps, k=10):
     Differentiable in mu and sigma.
     """
     return _ops.SO3Reparam.apply(mu, sigma, eps, k)
+
+
+def so3_reparameterize_eazyz(mu, sigma, eps, k=10):
+    """``group_matrix_to_eazyz(so3_reparameterize(...)[0])`` and the log-density in ONE kernel.
+
+    Returns the ZYZ Euler angles (n,B,3) of the sampled pose -- what ``VAE.decode`` passes to the action
+    decoder (``experiments/vae.py:182``) -- and log q (n,B); the 3x3 pose never leaves registers.
+    Differentiable in mu and sigma.
+    """
+    return _ops.SO3ReparamEazyz.apply(mu, sigma, eps, k)
 
 
 class N0reparameterize(nn.Module):
