@@ -345,8 +345,8 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "wigner_bwd_tma_kernel<10,8> (+ row-reduction kernels)", "achieved": kernels[dom]["gbs"], "peak": peak,
                          "unit": "GB/s", "frac": kernels[dom]["frac"],
                          # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture
-                         # profiles/r01_ncu_wigner_v2_summary.txt (852.63 MB + 7.61 MB at 2^18 samples per launch)
-                         "traffic": 860.24e6 * (micro / 262144.0), "peak_source": peak_src,
+                         # profiles/r01_ncu_wigner_v3_summary.txt (852.56 MB + 8.06 MB at 2^18 samples per launch)
+                         "traffic": 860.62e6 * (micro / 262144.0), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": abytes[dom] * micro},
             "pipeline_roofline": {"bytes_per_sample": 6656, "achieved_gbs": round(value / world * 6656 / 1e9, 1),
                                   "frac": round(value / world * 6656 / 1e9 / peak, 4)},

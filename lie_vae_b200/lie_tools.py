@@ -86,6 +86,16 @@ def quaternions_to_group_matrix(q):
     return _ops.QuatToMat.apply(q)
 
 
+def _z_rot_mat(angle, l):
+    """X_l(angle): diag cos(m*angle), anti-diag sin(m*angle), m = l..-l by row   (``lie_tools.py:195-208``).
+
+    Private helper of the reference (only ``wigner_d_matrix`` uses it); provided for completeness as
+    D^l(angle, 0, 0) = X(angle) J X(0) J X(0) = X(angle).
+    """
+    zeros = torch.zeros_like(angle)
+    return wigner_d_matrix(torch.stack([angle, zeros, zeros], -1), l)
+
+
 def _check_degree(l):
     if l > MAX_DEGREE:
         raise NotImplementedError("degree %d > %d is not supported by the sm_100a Wigner kernels" % (l, MAX_DEGREE))

@@ -393,3 +393,10 @@ def test_fused_reparam_eazyz(mods, k, n, B):
     as_good_as_ref32(lf, l64, l32, "log_q")
     as_good_as_ref32(gmf, gm64, gm32, "g_mu")
     as_good_as_ref32(gsf, gs64, gs32, "g_sigma")
+
+
+def test_z_rot_mat(mods):
+    lt, _, _ = mods
+    ang = torch.tensor([0.3, -1.2, 2.5], device="cuda")
+    for l in (0, 1, 4, 8):
+        close(lt._z_rot_mat(ang, l), O.z_rot_mat(ang.double().cpu(), l), 1e-5, 2e-6)
