@@ -206,14 +206,15 @@ def run_ours(args):
     red = torch.zeros(1 + M * CHANNELS, device=dev)
     step_obj = FusedSO3ActionStep(n_loc, micro, L_MAX, CHANNELS, K_WIND, device=dev)
 
+    g_item = step_obj.g_item          # the micro-batches accumulate into one gradient (no per-micro-batch add kernel)
+
     def one_step():
         g_item.zero_()
         step_obj.latent_forward(mu, sigma, eps, log_q)
         for i in range(n_micro):
             lo, hi = i * micro, (i + 1) * micro
             step_obj.decode_forward(lo, hi, item, y[i % 2])
-            step_obj.decode_backward(lo, hi, item, gy[i % NBUF])
-            g_item.add_(step_obj.g_item)
+            step_obj.decode_backward(lo, hi, item, gy[i % NBUF], accumulate=True)
         step_obj.latent_backward(mu, sigma, eps, glq, g_mu, g_sigma)
         # loss = sum(y * g_y) + sum(log_q * g_lq);  y is linear in item_rep, so sum(y * g_y) = <item_rep, grad item_rep>
         red[0] = (item * g_item).sum() + torch.dot(log_q, glq)

@@ -123,7 +123,8 @@ int lv_so3_reparam_eazyz_bwd_f32(const float* mu, const float* sigma, const floa
  *   _z_rot_mat lie_tools.py:195-208, ActionNet.forward decoders.py:47-56.
  *   M = (lmax+1)^2 - lmin^2.  angles (N,3); out (N,M,C).
  *   shared_spectrum != 0: spectrum is (M,C), the same for every sample (ActionNet.item_rep);
- *   otherwise (N,M,C).  transpose != 0 applies D^T (lie_tools.py:249-250).
+ *   otherwise (N,M,C).  Backward only: shared_spectrum = 3 (bit 1 set) ADDS the batch sum to gspectrum instead
+ *   of overwriting it (micro-batched steps accumulate one gradient).  transpose != 0 applies D^T (lie_tools.py:249-250).
  *   Backward: gout (N,M,C) -> gangles (N,3) and gspectrum ((M,C) summed over N if shared, else
  *   (N,M,C)).  The shared case needs `workspace` of lv_wigner_bwd_workspace_floats(...) floats
  *   (deterministic two-pass batch reduction, no atomics). ---- */

@@ -476,9 +476,9 @@ wigner_bwd_tma_kernel(const float* __restrict__ angles, const float* __restrict_
     }
 }
 
-// partial [nblk][MC] -> out[MC]; block = (32, 8): 32 consecutive columns, 8-way split over rows.
+// partial [nblk][MC] -> out[MC] (accumulate: out += ...); block = (32, 8): 32 consecutive columns, 8-way split over rows.
 __global__ void __launch_bounds__(256)
-wigner_reduce_partials(const float* __restrict__ partial, float* __restrict__ out, int nblk, int MC) {
+wigner_reduce_partials(const float* __restrict__ partial, float* __restrict__ out, int nblk, int MC, int accumulate) {
     __shared__ float red[8][33];
     const int o = blockIdx.x * 32 + threadIdx.x;
     float acc = 0.f;
@@ -490,7 +490,7 @@ wigner_reduce_partials(const float* __restrict__ partial, float* __restrict__ ou
         float a = 0.f;
 #pragma unroll
         for (int y = 0; y < 8; ++y) a += red[y][threadIdx.x];
-        out[o] = a;
+        out[o] = accumulate ? out[o] + a : a;
     }
 }
 
@@ -587,7 +587,8 @@ static int64_t tma_bwd_workspace_rows(int sms) { return int64_t(sms) * WQ_GROUPS
 
 template <int LT>
 static int launch_bwd_tma(const WgGeom& g, const float* angles, const float* spectrum, const float* gout, float* gangles,
-                          float* gspectrum, float* workspace, int64_t workspace_floats, int64_t N, int transpose, cudaStream_t st) {
+                          float* gspectrum, float* workspace, int64_t workspace_floats, int64_t N, int transpose, int accumulate,
+                          cudaStream_t st) {
     constexpr int C = 10, MC = (LT + 1) * (LT + 1) * C;
     if (!workspace || workspace_floats < tma_bwd_workspace_rows(g.sms) * MC) {
         set_error("wigner_apply_bwd: workspace of %lld floats required", (long long)(tma_bwd_workspace_rows(g.sms) * MC));
@@ -612,7 +613,7 @@ static int launch_bwd_tma(const WgGeom& g, const float* angles, const float* spe
         if (rc) return rc;
         rows += tail_grid;
     }
-    wigner_reduce_partials<<<(MC + 31) / 32, dim3(32, 8), 0, st>>>(partial, gspectrum, rows, MC);
+    wigner_reduce_partials<<<(MC + 31) / 32, dim3(32, 8), 0, st>>>(partial, gspectrum, rows, MC, accumulate);
     return check_launch("wigner_reduce_partials");
 }
 
@@ -658,8 +659,10 @@ extern "C" int lv_wigner_apply_bwd_f32(const float* angles, const float* spectru
     if (rc) return rc;
     if (!gspectrum) { lv::set_error("wigner_apply_bwd: null pointer"); return LV_ERR_ARG; }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int accumulate = (shared_spectrum & 2) ? 1 : 0;     // bit 1: gspectrum += batch sum (micro-batched steps)
+    if (accumulate && !(shared_spectrum & 1)) { lv::set_error("wigner_apply_bwd: accumulate needs a shared spectrum"); return LV_ERR_ARG; }
     if (N == 0) {
-        if (shared_spectrum) {
+        if (shared_spectrum && !accumulate) {
             cudaError_t e = cudaMemsetAsync(gspectrum, 0, size_t(g.MC) * 4, st);
             if (e != cudaSuccess) { lv::set_error("wigner_apply_bwd: memset: %s", cudaGetErrorString(e)); return int(e); }
         }
@@ -668,13 +671,13 @@ extern "C" int lv_wigner_apply_bwd_f32(const float* angles, const float* spectru
     if (!angles || !spectrum || !gout || !gangles) { lv::set_error("wigner_apply_bwd: null pointer"); return LV_ERR_ARG; }
     int grid = 0;
     if (shared_spectrum && lv::tma_bwd_eligible(C, lmin, lmax, gout, N)) {
-        if (lmax == 8) return lv::launch_bwd_tma<8>(g, angles, spectrum, gout, gangles, gspectrum, workspace, workspace_floats, N, transpose, st);
-        return lv::launch_bwd_tma<6>(g, angles, spectrum, gout, gangles, gspectrum, workspace, workspace_floats, N, transpose, st);
+        if (lmax == 8) return lv::launch_bwd_tma<8>(g, angles, spectrum, gout, gangles, gspectrum, workspace, workspace_floats, N, transpose, accumulate, st);
+        return lv::launch_bwd_tma<6>(g, angles, spectrum, gout, gangles, gspectrum, workspace, workspace_floats, N, transpose, accumulate, st);
     }
     if (shared_spectrum) {
         rc = WG_DISPATCH(C, lmin, lmax, true, lv::launch_bwd, g, angles, spectrum, gout, gangles, gspectrum, workspace, workspace_floats, N, lmin, lmax, C, transpose, st, &grid);
         if (rc) return rc;
-        lv::wigner_reduce_partials<<<(g.MC + 31) / 32, dim3(32, 8), 0, st>>>(workspace, gspectrum, grid, g.MC);
+        lv::wigner_reduce_partials<<<(g.MC + 31) / 32, dim3(32, 8), 0, st>>>(workspace, gspectrum, grid, g.MC, accumulate);
         return lv::check_launch("wigner_reduce_partials");
     }
     return WG_DISPATCH(C, lmin, lmax, false, lv::launch_bwd, g, angles, spectrum, gout, gangles, gspectrum, workspace, workspace_floats, N, lmin, lmax, C, transpose, st, &grid);

@@ -89,12 +89,13 @@ class FusedSO3ActionStep:
         self._timed("wigner_fwd", lambda: _cabi.call("lv_wigner_apply_fwd_f32", p(self.angles[lo:hi]), p(item_rep), p(y), hi - lo, 0, self.L,
                                                     self.C, 1, int(self.transpose), st))
 
-    def decode_backward(self, lo, hi, item_rep, g_y):
-        """g_y (hi-lo, M, C) -> g_angles[lo:hi] and self.g_item (M,C) for this micro-batch."""
+    def decode_backward(self, lo, hi, item_rep, g_y, accumulate=False):
+        """g_y (hi-lo, M, C) -> g_angles[lo:hi] and self.g_item (M,C): the gradient of this micro-batch, or, with
+        ``accumulate``, added to what self.g_item already holds (zero it at the start of a step)."""
         st, p = _stream(), _cabi.ptr
         self._timed("wigner_bwd", lambda: _cabi.call("lv_wigner_apply_bwd_f32", p(self.angles[lo:hi]), p(item_rep), p(g_y), p(self.g_angles[lo:hi]),
-                                                    p(self.g_item), p(self.workspace), self.nws, hi - lo, 0, self.L, self.C, 1,
-                                                    int(self.transpose), st))
+                                                    p(self.g_item), p(self.workspace), self.nws, hi - lo, 0, self.L, self.C,
+                                                    3 if accumulate else 1, int(self.transpose), st))
 
     def latent_backward(self, mu, sigma, eps, g_log_q, g_mu, g_sigma, g_z=None):
         """g_angles (from decode_backward), g_log_q (B) and optionally g_z (B,3,3) -> g_mu (B,3,3), g_sigma (B,3)."""

@@ -400,3 +400,28 @@ def test_z_rot_mat(mods):
     ang = torch.tensor([0.3, -1.2, 2.5], device="cuda")
     for l in (0, 1, 4, 8):
         close(lt._z_rot_mat(ang, l), O.z_rot_mat(ang.double().cpu(), l), 1e-5, 2e-6)
+
+
+@pytest.mark.parametrize("L,C,N", [(8, 10, 4112), (3, 3, 500)])
+def test_wigner_backward_accumulate_flag(mods, L, C, N):
+    """shared_spectrum = 3 adds the batch sum to gspectrum (TMA-fed and cp.async kernels): two micro-batches accumulated
+    through the pipeline runner equal one call over the concatenated batch."""
+    from lie_vae_b200.pipeline import FusedSO3ActionStep
+    from lie_vae_b200 import _ops
+    torch.manual_seed(9)
+    M = (L + 1) ** 2
+    ang = torch.rand(N, 3, device="cuda") * 6 - 3
+    item = torch.randn(M, C, device="cuda")
+    g = torch.randn(N, M, C, device="cuda")
+    a, it = ang.clone().requires_grad_(True), item.clone().requires_grad_(True)
+    _ops.WignerApply.apply(a, it, 0, L, False).backward(g)
+    half = (N // 32) * 16
+    step = FusedSO3ActionStep(N, N, L, C, 3, device="cuda")
+    step.angles.copy_(ang)
+    step.g_item.zero_()
+    step.decode_backward(0, half, item, g[:half].contiguous(), accumulate=True)
+    step.decode_backward(half, N, item, g[half:].contiguous(), accumulate=True)
+    assert torch.equal(step.g_angles, a.grad)
+    assert (step.g_item - it.grad).abs().max().item() <= 2e-6 * it.grad.abs().max().item()
+    step.decode_backward(0, N, item, g, accumulate=False)          # overwrite mode ignores what was there
+    assert (step.g_item - it.grad).abs().max().item() <= 2e-6 * it.grad.abs().max().item()
