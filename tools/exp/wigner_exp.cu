@@ -493,20 +493,20 @@ bwd2_kernel(const float* __restrict__ angles, const float* __restrict__ spectrum
     float* s_item = s_gp + S * CP * 3 + 4;
     const int t = threadIdx.x;
     const int s = t / CP, p = t - s * CP;
-    if (ITEM_SMEM) for (int o = t; o < MC; o += blockDim.x) s_item[o] = __ldg(spectrum + o);
+    if (ITEM_SMEM & 1) for (int o = t; o < MC; o += blockDim.x) s_item[o] = __ldg(spectrum + o);
     // per-thread column accumulators: quads q = t, t + blockDim, ... (MC = 810 -> 203 quads, <= 2 per thread at 160 threads)
     float4 acc_a = make_float4(0.f, 0.f, 0.f, 0.f), acc_b = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int64_t tile_idx = blockIdx.x; tile_idx < ntiles; tile_idx += gridDim.x) {
         const int64_t n0 = tile_idx * S;
         const int rows = int(min(int64_t(S), N - n0));
-        tile_g2s(tile, gout + n0 * MC, rows * MC);
+        if (!(ITEM_SMEM & 2)) tile_g2s(tile, gout + n0 * MC, rows * MC);
         stage_trig(s_trig, angles, n0, rows);
         tile_async_wait();
         __syncthreads();
         if (s < rows) {
             const float2* tg = reinterpret_cast<const float2*>(s_trig + s * TS);
             f32x2_t* trow = reinterpret_cast<f32x2_t*>(tile + s * MC) + p;
-            const f32x2_t* srow = reinterpret_cast<const f32x2_t*>(ITEM_SMEM ? s_item : spectrum) + p;
+            const f32x2_t* srow = reinterpret_cast<const f32x2_t*>((ITEM_SMEM & 1) ? s_item : spectrum) + p;
             f32x2_t acc[6] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
             degrees_bwd2_from<0>(srow, trow, tg, acc);
             const float2 a0 = vunpack(acc[0]), a1 = vunpack(acc[1]), b0 = vunpack(acc[2]), b1 = vunpack(acc[3]), c0 = vunpack(acc[4]), c1 = vunpack(acc[5]);
@@ -515,7 +515,7 @@ bwd2_kernel(const float* __restrict__ angles, const float* __restrict__ spectrum
             s_gp[t * 3 + 2] = (c0.x - c1.x) + (c0.y - c1.y);
         }
         __syncthreads();
-        {
+        if (!(ITEM_SMEM & 4)) {
             // column sums into registers: thread owns quads t and t + blockDim.x
             for (int k = 0; k < 2; ++k) {
                 const int q = t + k * blockDim.x;
@@ -548,7 +548,7 @@ bwd2_kernel(const float* __restrict__ angles, const float* __restrict__ spectrum
 
 template <int ITEM_SMEM, int MINB>
 static int launch_b2(const float* angles, const float* spectrum, const float* gout, float* gangles, float* partial, int64_t N, int S, int grid, cudaStream_t st) {
-    const size_t smem = size_t(S * MC + S * TS + S * CP * 3 + 4 + (ITEM_SMEM ? MC : 0)) * 4;
+    const size_t smem = size_t(S * MC + S * TS + S * CP * 3 + 4 + ((ITEM_SMEM & 1) ? MC : 0)) * 4;
     cudaError_t e = cudaFuncSetAttribute(bwd2_kernel<ITEM_SMEM, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     if (e != cudaSuccess) return int(e);
     bwd2_kernel<ITEM_SMEM, MINB><<<grid, S * CP, smem, st>>>(angles, spectrum, gout, gangles, partial, N, S, (N + S - 1) / S);
@@ -561,6 +561,7 @@ extern "C" int exp_wigner_bwd2(int var, const float* angles, const float* spectr
         case 0: return launch_b2<0, 2>(angles, spectrum, gout, gangles, partial, N, S, grid, st);
         case 1: return launch_b2<1, 1>(angles, spectrum, gout, gangles, partial, N, S, grid, st);
         case 2: return launch_b2<0, 1>(angles, spectrum, gout, gangles, partial, N, S, grid, st);
+        case 6: return launch_b2<6, 2>(angles, spectrum, gout, gangles, partial, N, S, grid, st);
         default: return -1;
     }
 }
