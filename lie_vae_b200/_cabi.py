@@ -11,7 +11,7 @@ import re
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liblievae_sm100a.so")
+LIB_PATH = os.environ.get("LIEVAE_LIB") or os.path.join(HERE, "liblievae_sm100a.so")   # override: tools/exp variants only
 HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "lievae.h")
 
 _lock = threading.Lock()

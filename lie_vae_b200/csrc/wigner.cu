@@ -39,113 +39,96 @@
 // transpose=True (lie_tools.py:249-250): D^T = X(-c) J X(-b) J X(-a), i.e. the same kernels on
 // the angles (-c, -b, -a), with the angle gradients mapped back.
 #include "common.cuh"
-#include "wigner_gen.cuh"
+#include "wigner_gen2.cuh"
 
 namespace lv {
 
-constexpr int WG_LMAX = wg::kGenLmax;
+constexpr int WG_LMAX = wg2::kGenLmax;
 constexpr int WG_TRIG_STRIDE = 52;   // 3 angles x 8 x (cos,sin) = 48 floats, padded: 16B-aligned rows, 4 samples on distinct bank quads
 constexpr int WG_MAX_THREADS = 256;
 constexpr int WG_MAX_CTAS_PER_SM = 8;   // bound used to size the backward workspace
 
-using wg::jmul;
+using wg2::PDeg;
+using wg2::f32x2_t;
 
-// pair rotations: x <- X(phi) x          (lie_tools.py:195-208: X[i,i]=cos((l-i)phi), X[i,2l-i]=sin((l-i)phi))
-// cs[m-1] = (cos m phi, sin m phi); two frequencies per 128-bit LDS.  TRANSPOSED: X(phi)^T = X(-phi).
-template <int L, bool TRANSPOSED>
-__device__ __forceinline__ void xrot(float (&x)[2 * L + 1], const float2* __restrict__ cs) {
-    const float4* cs4 = reinterpret_cast<const float4*>(cs);
+// Per-sample trig table: 3 angles x 4 float4 slots; slot q of an angle holds (cos m1 phi, cos m2 phi, sin m1 phi, sin m2 phi)
+// for the frequency pairs (1,3) (5,7) (2,4) (6,8) -- the pairing of wigner_gen2.cuh, so that a pair rotation
+// (lie_tools.py:195-208: X[i,i] = cos((l-i)phi), X[i,2l-i] = sin((l-i)phi)) reads its operands with one LDS.128.
+constexpr int WG_TRIG_ANGLE = 16;   // floats per angle
+__device__ __forceinline__ int trig_index(int m) {      // float offset of cos(m phi) inside an angle's block; sin is +2
+    return (m & 1) ? ((m - 1) >> 2) * 4 + (((m - 1) >> 1) & 1) : 8 + ((m - 2) >> 2) * 4 + (((m - 2) >> 1) & 1);
+}
+// cos/sin(m * phi), m = 1..WG_LMAX, by sincosf + angle-addition recurrence, written in table order
+__device__ __forceinline__ void trig_fill(float* __restrict__ dst, float phi) {
+    float s1, c1;
+    sincosf(phi, &s1, &c1);
+    float cm = c1, sm = s1;
 #pragma unroll
-    for (int p = 0; p < (L + 1) / 2; ++p) {
-        float4 t = cs4[p];
-        if (TRANSPOSED) { t.y = -t.y; t.w = -t.w; }
-        {
-            const int m = 2 * p + 1;
-            const float a = x[L - m], b = x[L + m];
-            x[L - m] = fmaf(t.x, a, t.y * b);
-            x[L + m] = fmaf(t.x, b, -(t.y * a));
-        }
-        if (2 * p + 2 <= L) {
-            const int m = 2 * p + 2;
-            const float a = x[L - m], b = x[L + m];
-            x[L - m] = fmaf(t.z, a, t.w * b);
-            x[L + m] = fmaf(t.z, b, -(t.w * a));
-        }
+    for (int m = 1; m <= WG_LMAX; ++m) {
+        dst[trig_index(m)] = cm;
+        dst[trig_index(m) + 2] = sm;
+        const float cn = fmaf(cm, c1, -(sm * s1));
+        sm = fmaf(sm, c1, cm * s1);
+        cm = cn;
     }
 }
-// <h, G w> = sum_m m (h[l-m] w[l+m] - h[l+m] w[l-m])
-template <int L>
-__device__ __forceinline__ float gdot(const float (&h)[2 * L + 1], const float (&w)[2 * L + 1]) {
-    float acc = 0.f;
-#pragma unroll
-    for (int m = 1; m <= L; ++m) acc = fmaf(float(m), fmaf(h[L - m], w[L + m], -(h[L + m] * w[L - m])), acc);
-    return acc;
-}
 
-// cos/sin(m * angle), m = 1..WG_LMAX, for the CTA's samples.  trig[s][a][m-1] = (cos, sin);
-// a = 0,1,2 are the *effective* first/second/third angles (transpose: (-c,-b,-a)).
+// cos/sin(m * angle) for the CTA's samples.  trig[s][a] with a = 0,1,2 the *effective* first/second/third
+// angles (transpose: (-c,-b,-a)).
 __device__ __forceinline__ void stage_trig(float* __restrict__ s_trig, const float* __restrict__ angles, int64_t n0,
                                            int rows, int transpose) {
     for (int j = threadIdx.x; j < rows * 3; j += blockDim.x) {
         const int s = j / 3, a = j - 3 * s;
         const float phi = transpose ? -__ldg(angles + (n0 + s) * 3 + (2 - a)) : __ldg(angles + n0 * 3 + j);
-        float s1, c1;
-        sincosf(phi, &s1, &c1);
-        float2* dst = reinterpret_cast<float2*>(s_trig + s * WG_TRIG_STRIDE + a * (2 * WG_LMAX));
-        float cm = c1, sm = s1;
-#pragma unroll
-        for (int m = 1; m <= WG_LMAX; ++m) {
-            dst[m - 1] = make_float2(cm, sm);
-            const float cn = fmaf(cm, c1, -(sm * s1));
-            sm = fmaf(sm, c1, cm * s1);
-            cm = cn;
-        }
+        trig_fill(s_trig + s * WG_TRIG_STRIDE + a * WG_TRIG_ANGLE, phi);
     }
 }
 
+// y_l = X(a) J X(b) J X(c) s_l on one column; tg = the sample's trig table (angle a at +0, b at +4, c at +8 float4)
 template <int L, bool GLOBAL_SRC>
-__device__ __forceinline__ void load_col(float (&x)[2 * L + 1], const float* __restrict__ src, int stride) {
-#pragma unroll
-    for (int i = 0; i < 2 * L + 1; ++i) x[i] = GLOBAL_SRC ? __ldg(src + i * stride) : src[i * stride];
+__device__ __forceinline__ void degree_fwd(const float* src, float* dst, int C, const float4* __restrict__ tg) {
+    using D = PDeg<L>;
+    typename D::Vec x, y;
+    D::template load<GLOBAL_SRC>(x, src, C);
+    D::template xrot<false>(x, tg + 8);
+    D::jmul(x, y);
+    D::template xrot<false>(y, tg + 4);
+    D::jmul(y, x);
+    D::template xrot<false>(x, tg);
+    D::store(x, dst, C);
 }
 
-template <int L, bool GLOBAL_SRC>
-__device__ __forceinline__ void degree_fwd(const float* src, float* dst, int C, const float2* __restrict__ tg) {
-    float x[2 * L + 1], y[2 * L + 1];
-    load_col<L, GLOBAL_SRC>(x, src, C);
-    xrot<L, false>(x, tg + 2 * WG_LMAX);
-    jmul<L>(x, y);
-    xrot<L, false>(y, tg + WG_LMAX);
-    jmul<L>(y, x);
-    xrot<L, false>(x, tg);
-#pragma unroll
-    for (int i = 0; i < 2 * L + 1; ++i) dst[i * C] = x[i];
-}
+// angle-gradient accumulators: one packed pair (summed over its lanes at the end) and one scalar per angle
+struct AngleAcc {
+    f32x2_t pa = 0ull, pb = 0ull, pc = 0ull;
+    float sa = 0.f, sb = 0.f, sc = 0.f;
+    __device__ __forceinline__ float ga() const { return sa + (wg2::plo(pa) + wg2::phi(pa)); }
+    __device__ __forceinline__ float gb() const { return sb + (wg2::plo(pb) + wg2::phi(pb)); }
+    __device__ __forceinline__ float gc() const { return sc + (wg2::plo(pc) + wg2::phi(pc)); }
+};
 
 // g (smem tile column): upstream gradient in, spectrum gradient out (in place).
 template <int L, bool GLOBAL_SRC>
-__device__ __forceinline__ void degree_bwd(const float* src, float* g, int C, const float2* __restrict__ tg,
-                                           float& ga, float& gb, float& gc) {
-    float x[2 * L + 1], y[2 * L + 1], w2[2 * L + 1];
-    load_col<L, GLOBAL_SRC>(x, src, C);
-    xrot<L, false>(x, tg + 2 * WG_LMAX);
-    jmul<L>(x, w2);
-#pragma unroll
-    for (int i = 0; i < 2 * L + 1; ++i) y[i] = w2[i];
-    xrot<L, false>(y, tg + WG_LMAX);
-    jmul<L>(y, x);                            // x = w4
-    load_col<L, false>(y, g, C);              // y = g
-    xrot<L, true>(y, tg);                     // h4
-    ga += gdot<L>(y, x);
-    jmul<L>(y, x);                            // x = h3
-    xrot<L, true>(x, tg + WG_LMAX);           // h2
-    gb += gdot<L>(x, w2);
-    jmul<L>(x, y);                            // y = h1
-    xrot<L, true>(y, tg + 2 * WG_LMAX);       // g_s
-    load_col<L, GLOBAL_SRC>(x, src, C);
-    gc += gdot<L>(y, x);
-#pragma unroll
-    for (int i = 0; i < 2 * L + 1; ++i) g[i * C] = y[i];
+__device__ __forceinline__ void degree_bwd(const float* src, float* g, int C, const float4* __restrict__ tg, AngleAcc& acc) {
+    using D = PDeg<L>;
+    typename D::Vec x, y, w2;
+    D::template load<GLOBAL_SRC>(x, src, C);
+    D::template xrot<false>(x, tg + 8);
+    D::jmul(x, w2);
+    y = w2;
+    D::template xrot<false>(y, tg + 4);
+    D::jmul(y, x);                                   // x = w4
+    D::template load<false>(y, g, C);                // y = g
+    D::template xrot<true>(y, tg);                   // h4
+    D::gdot(y, x, acc.pa, acc.sa);
+    D::jmul(y, x);                                   // x = h3
+    D::template xrot<true>(x, tg + 4);               // h2
+    D::gdot(x, w2, acc.pb, acc.sb);
+    D::jmul(x, y);                                   // y = h1
+    D::template xrot<true>(y, tg + 8);               // g_s
+    D::template load<GLOBAL_SRC>(x, src, C);
+    D::gdot(y, x, acc.pc, acc.sc);
+    D::store(y, g, C);
 }
 
 #define WG_SWITCH(l, CALL)                      \
@@ -164,12 +147,12 @@ __device__ __forceinline__ void degree_bwd(const float* src, float* g, int C, co
 // all degrees of one column.  LT >= 0: degrees 0..LT, fully unrolled (offsets l^2*C are constants);
 // LT < 0: run-time range lmin..lmax.
 template <int L, int LT, bool GLOBAL_SRC>
-__device__ __forceinline__ void fwd_unrolled(const float* srow, float* trow, int C, const float2* tg) {
+__device__ __forceinline__ void fwd_unrolled(const float* srow, float* trow, int C, const float4* tg) {
     degree_fwd<L, GLOBAL_SRC>(srow + L * L * C, trow + L * L * C, C, tg);
     if constexpr (L < LT) fwd_unrolled<L + 1, LT, GLOBAL_SRC>(srow, trow, C, tg);
 }
 template <int LT, bool GLOBAL_SRC>
-__device__ __forceinline__ void fwd_degrees(const float* srow, float* trow, int C, const float2* tg, int lmin, int lmax) {
+__device__ __forceinline__ void fwd_degrees(const float* srow, float* trow, int C, const float4* tg, int lmin, int lmax) {
     if constexpr (LT >= 0) {
         fwd_unrolled<0, LT, GLOBAL_SRC>(srow, trow, C, tg);
     } else {
@@ -181,19 +164,19 @@ __device__ __forceinline__ void fwd_degrees(const float* srow, float* trow, int 
     }
 }
 template <int L, int LT, bool GLOBAL_SRC>
-__device__ __forceinline__ void bwd_unrolled(const float* srow, float* trow, int C, const float2* tg, float& ga, float& gb, float& gc) {
-    degree_bwd<L, GLOBAL_SRC>(srow + L * L * C, trow + L * L * C, C, tg, ga, gb, gc);
-    if constexpr (L < LT) bwd_unrolled<L + 1, LT, GLOBAL_SRC>(srow, trow, C, tg, ga, gb, gc);
+__device__ __forceinline__ void bwd_unrolled(const float* srow, float* trow, int C, const float4* tg, AngleAcc& acc) {
+    degree_bwd<L, GLOBAL_SRC>(srow + L * L * C, trow + L * L * C, C, tg, acc);
+    if constexpr (L < LT) bwd_unrolled<L + 1, LT, GLOBAL_SRC>(srow, trow, C, tg, acc);
 }
 template <int LT, bool GLOBAL_SRC>
-__device__ __forceinline__ void bwd_degrees(const float* srow, float* trow, int C, const float2* tg, int lmin, int lmax,
-                                            float& ga, float& gb, float& gc) {
+__device__ __forceinline__ void bwd_degrees(const float* srow, float* trow, int C, const float4* tg, int lmin, int lmax,
+                                            AngleAcc& acc) {
     if constexpr (LT >= 0) {
-        bwd_unrolled<0, LT, GLOBAL_SRC>(srow, trow, C, tg, ga, gb, gc);
+        bwd_unrolled<0, LT, GLOBAL_SRC>(srow, trow, C, tg, acc);
     } else {
         int off = 0;
         for (int l = lmin; l <= lmax; ++l) {
-            WG_SWITCH(l, (degree_bwd<L, GLOBAL_SRC>(srow + off, trow + off, C, tg, ga, gb, gc)));
+            WG_SWITCH(l, (degree_bwd<L, GLOBAL_SRC>(srow + off, trow + off, C, tg, acc)));
             off += (2 * l + 1) * C;
         }
     }
@@ -226,7 +209,7 @@ wigner_fwd_kernel(const float* __restrict__ angles, const float* __restrict__ sp
     const int t = threadIdx.x;
     const int s = t / C, c = t - s * C;
     if (s < rows) {
-        const float2* tg = reinterpret_cast<const float2*>(s_trig + s * WG_TRIG_STRIDE);
+        const float4* tg = reinterpret_cast<const float4*>(s_trig + s * WG_TRIG_STRIDE);
         float* trow = tile + s * MC + c;
         // shared spectrum: 3 KB read by every thread of every CTA -> stays L1-resident (the kernel streams
         // nothing else through L1: outputs leave through smem), so it is read in place with LDG.
@@ -281,11 +264,12 @@ wigner_bwd_kernel(const float* __restrict__ angles, const float* __restrict__ sp
         tile_async_wait();
         __syncthreads();
         if (s < rows) {
-            const float2* tg = reinterpret_cast<const float2*>(s_trig + s * WG_TRIG_STRIDE);
+            const float4* tg = reinterpret_cast<const float4*>(s_trig + s * WG_TRIG_STRIDE);
             float* trow = tile + s * MC + c;
             const float* srow = SHARED ? s_item + c : spectrum + (n0 + s) * MC + c;
-            float ga = 0.f, gb = 0.f, gc = 0.f;
-            bwd_degrees<LT, !SHARED>(srow, trow, C, tg, lmin, lmax, ga, gb, gc);
+            AngleAcc acc;
+            bwd_degrees<LT, !SHARED>(srow, trow, C, tg, lmin, lmax, acc);
+            const float ga = acc.ga(), gb = acc.gb(), gc = acc.gc();
             // effective angles (a',b',c') = transpose ? (-c,-b,-a) : (a,b,c)
             s_gp[t * 3 + 0] = transpose ? -gc : ga;
             s_gp[t * 3 + 1] = transpose ? -gb : gb;
@@ -342,7 +326,22 @@ wigner_bwd_kernel(const float* __restrict__ angles, const float* __restrict__ sp
 // the math groups never execute a copy loop or a reduction loop and never wait for HBM in steady state.  Each accumulator
 // element receives exactly one add per tile, in tile order: the batch sum stays run-to-run reproducible.
 // Requires full 16-sample tiles and 16-byte aligned g_y (the host sends a ragged tail through wigner_bwd_kernel).
-constexpr int WQ_S = 16, WQ_GROUPS = 3, WQ_BUFS = 4, WQ_GT = 160, WQ_THREADS = WQ_GROUPS * WQ_GT;
+#ifndef WQ_GROUPS_N
+#define WQ_GROUPS_N 3
+#endif
+#ifndef WQ_ITEM_SMEM
+#define WQ_ITEM_SMEM 0
+#endif
+#ifndef WQ_USE_GROUPS      // 1: the group-barrier kernel (wigner_bwd_tma_kernel); 0: the warp-decoupled kernel
+#define WQ_USE_GROUPS 0
+#endif
+#ifndef WQ_L2_PREFETCH     // tiles ahead of the TMA load that are prefetched into L2 (0 = off)
+#define WQ_L2_PREFETCH 0
+#endif
+#ifndef WQ_ABLATE          // experiments only (tools/exp/variant.py): 1 no reduce-add, 2 plain store instead, 4 no math
+#define WQ_ABLATE 0
+#endif
+constexpr int WQ_S = 16, WQ_GROUPS = WQ_GROUPS_N, WQ_BUFS = 4, WQ_GT = 160, WQ_THREADS = WQ_GROUPS * WQ_GT;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -374,6 +373,7 @@ wigner_bwd_tma_kernel(const float* __restrict__ angles, const float* __restrict_
     // barrier per buffer a group that runs two uses ahead of a starved group would see the 1-bit phase parity of the
     // previous use and walk into a buffer that is still being computed on.
     uint64_t* full = reinterpret_cast<uint64_t*>(gp_all + WQ_GROUPS * WQ_GT * 3);   // [4][2]
+    float* s_item = reinterpret_cast<float*>(full + 2 * WQ_BUFS);                   // [MC] (WQ_ITEM_SMEM)
     const int tid = threadIdx.x, g = tid / WQ_GT, t = tid - g * WQ_GT;
     const int s = t / C, c = t - s * C;
     float* s_trig = trig_all + g * WQ_S * WG_TRIG_STRIDE;
@@ -386,6 +386,7 @@ wigner_bwd_tma_kernel(const float* __restrict__ angles, const float* __restrict_
         for (int b = 0; b < 2 * WQ_BUFS; ++b) mbar_init(full + b, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (WQ_ITEM_SMEM) for (int o = tid; o < MC; o += WQ_THREADS) s_item[o] = __ldg(spectrum + o);
     __syncthreads();
     if (tid == 0) {
         for (int j = 0; j < WQ_BUFS && j < my_tiles; ++j) {
@@ -404,31 +405,23 @@ wigner_bwd_tma_kernel(const float* __restrict__ angles, const float* __restrict_
         for (int q = t; q < WQ_S * 3; q += WQ_GT) {
             const int ss = q / 3, a = q - 3 * ss;
             const float phi = transpose ? -__ldg(angles + (n0 + ss) * 3 + (2 - a)) : __ldg(angles + n0 * 3 + q);
-            float s1, c1;
-            sincosf(phi, &s1, &c1);
-            float2* dst = reinterpret_cast<float2*>(s_trig + ss * WG_TRIG_STRIDE + a * (2 * WG_LMAX));
-            float cm = c1, sm = s1;
-#pragma unroll
-            for (int m = 1; m <= WG_LMAX; ++m) {
-                dst[m - 1] = make_float2(cm, sm);
-                const float cn = fmaf(cm, c1, -(sm * s1));
-                sm = fmaf(sm, c1, cm * s1);
-                cm = cn;
-            }
+            trig_fill(s_trig + ss * WG_TRIG_STRIDE + a * WG_TRIG_ANGLE, phi);
         }
-        mbar_wait(bar, parity);
-        named_bar_sync(1 + g, WQ_GT);
-        {
-            float ga = 0.f, gb = 0.f, gc = 0.f;
-            bwd_unrolled<0, LT, true>(spectrum + c, tile + s * MC + c, C, reinterpret_cast<const float2*>(s_trig + s * WG_TRIG_STRIDE), ga, gb, gc);
+        if (!(WQ_ABLATE & 32)) mbar_wait(bar, parity);
+        if (!(WQ_ABLATE & 16)) named_bar_sync(1 + g, WQ_GT);
+        if (!(WQ_ABLATE & 4)) {
+            AngleAcc acc;
+            bwd_unrolled<0, LT, !WQ_ITEM_SMEM>((WQ_ITEM_SMEM ? s_item : spectrum) + c, tile + s * MC + c, C, reinterpret_cast<const float4*>(s_trig + s * WG_TRIG_STRIDE), acc);
+            const float ga = acc.ga(), gb = acc.gb(), gc = acc.gc();
             s_gp[t * 3 + 0] = transpose ? -gc : ga;
             s_gp[t * 3 + 1] = transpose ? -gb : gb;
             s_gp[t * 3 + 2] = transpose ? -ga : gc;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy tile writes -> visible to the copy engine
-        named_bar_sync(1 + g, WQ_GT);
+        if (!(WQ_ABLATE & 8)) named_bar_sync(1 + g, WQ_GT);
         if (t == WQ_GT - 1) {      // a lane that neither builds the trig table nor sums the angle gradients
-            if (j == g)
+            if (WQ_ABLATE & 1) {
+            } else if (j == g || (WQ_ABLATE & 2))
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                              :: "l"(acc), "r"(smem_u32(tile)), "r"(TILE_BYTES) : "memory");
             else
@@ -440,11 +433,14 @@ wigner_bwd_tma_kernel(const float* __restrict__ angles, const float* __restrict_
             else
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the engine has read the buffer: refill it
             const int64_t jn = j + WQ_BUFS;
-            if (jn < my_tiles) {
+            if (jn < my_tiles && !(WQ_ABLATE & 32)) {
                 uint64_t* nbar = full + 2 * buf + int((use + 1) & 1);
                 mbar_expect_tx(nbar, TILE_BYTES);
                 tma_load(tile, gout + (first + jn * stride) * WQ_S * MC, TILE_BYTES, nbar);
             }
+            if (WQ_L2_PREFETCH > 0 && jn + WQ_L2_PREFETCH < my_tiles)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
+                             :: "l"(gout + (first + (jn + WQ_L2_PREFETCH) * stride) * WQ_S * MC), "r"(TILE_BYTES) : "memory");
         }
         for (int q = t; q < WQ_S * 3; q += WQ_GT) {
             const int ss = q / 3, a = q - 3 * ss;
@@ -473,6 +469,175 @@ wigner_bwd_tma_kernel(const float* __restrict__ angles, const float* __restrict_
         }
     } else {
         for (int o = t; o < MC; o += WQ_GT) prow[o] = 0.f;      // a group without work contributes a zero row
+    }
+}
+
+// ------------------------------------------------------------------ backward, shared spectrum, warp-decoupled (sm_100a)
+// Same math as above, no group barriers.  One persistent 512-thread CTA per SM: 15 math warps and one producer warp,
+// four 16-sample tile buffers in a ring (tile q of the CTA lives in buffer q % 4).
+//   * work item = (tile q, slice p): 32 of the tile's 160 (sample, channel) columns.  Math warps pull items in order from a
+//     shared-memory counter, so a warp that runs ahead (the scheduler favours high warp ids; SMSP 3 hosts one math warp
+//     less) simply takes more items -- nobody waits at a barrier for the slowest warp of a group.
+//   * a math warp waits for full[q % 4] (TMA bytes landed + trig table written), runs the backward chain on its 32
+//     columns (spectrum gradient in place, angle-gradient parts to gp), and arrives on empty[q % 4] (count 5).
+//   * the producer warp (warp 15: highest scheduling priority, on the SMSP with a free slot) owns everything else.  For
+//     tile r, in ring order: wait empty -> column sums of the finished tile into 26 registers per lane (this IS the batch
+//     reduction of the item_rep gradient: no atomics, no L2 reduce traffic, fixed order -> bit-reproducible) -> sum the
+//     angle-gradient parts over the 10 channels and store g_angles -> TMA bulk load of tile r + 4 into the buffer (plus an
+//     L2 prefetch of the tile after it) -> write the trig table of tile r + 4, which it computed *before* the wait ->
+//     arrive on full.  The buffer's turnaround is column sums + one load latency; three tiles are being computed meanwhile.
+// Requires full 16-sample tiles and 16-byte aligned g_y (the host sends a ragged tail through wigner_bwd_kernel).
+#ifndef WD_MATH_WARPS_N
+#define WD_MATH_WARPS_N 14
+#endif
+constexpr int WD_S = 16, WD_BUFS = 4, WD_MATH_WARPS = WD_MATH_WARPS_N, WD_THREADS = (WD_MATH_WARPS + 2) * 32, WD_SLICES = 5;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int CT, int LT>
+__global__ void __launch_bounds__(WD_THREADS, 1)
+wigner_bwd_ws_kernel(const float* __restrict__ angles, const float* __restrict__ spectrum, const float* __restrict__ gout,
+                     float* __restrict__ gangles, float* __restrict__ partial, int64_t ntiles, int transpose) {
+    constexpr int C = CT, M = (LT + 1) * (LT + 1), MC = M * C, COLS = WD_S * C;     // COLS = 160 columns per tile
+    static_assert(COLS == WD_SLICES * 32, "a tile must split into whole warps");
+    static_assert(MC % 2 == 0, "column sums read float2");
+    constexpr uint32_t TILE_BYTES = WD_S * MC * 4u;
+    constexpr int NC2 = MC / 2, KACC = (NC2 + 63) / 64;                             // float2 columns, accumulators per lane
+    extern __shared__ __align__(16) float smem[];
+    float* tiles = smem;                                             // [4][16][MC]
+    float* trig_all = tiles + WD_BUFS * WD_S * MC;                   // [4][16][52]
+    float* gp_all = trig_all + WD_BUFS * WD_S * WG_TRIG_STRIDE;      // [4][160][3]
+    uint64_t* full = reinterpret_cast<uint64_t*>(gp_all + WD_BUFS * COLS * 3);      // [4]  count 3: expect_tx arrive + one trig arrive per producer warp
+    uint64_t* empty = full + WD_BUFS;                                               // [4]  count 5: one per slice
+    int* s_next = reinterpret_cast<int*>(empty + WD_BUFS);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t first = blockIdx.x, stride = gridDim.x;
+    const int64_t my_tiles = first < ntiles ? (ntiles - first + stride - 1) / stride : 0;
+    if (tid == 0) {
+        for (int b = 0; b < WD_BUFS; ++b) { mbar_init(full + b, 3); mbar_init(empty + b, WD_SLICES); }
+        *s_next = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp < WD_MATH_WARPS) {
+        // ------------------------------------------------------------ math warps
+        for (;;) {
+            int item = 0;
+            if (lane == 0) item = atomicAdd(s_next, 1);
+            item = __shfl_sync(0xffffffffu, item, 0);
+            const int64_t q = item / WD_SLICES;
+            if (q >= my_tiles) break;
+            const int p = item - int(q) * WD_SLICES;
+            const int buf = int(q) & (WD_BUFS - 1);
+            const int t = p * 32 + lane, s = t / C, c = t - s * C;
+            mbar_wait(full + buf, uint32_t(q >> 2) & 1u);
+            AngleAcc acc;
+            if (!(WQ_ABLATE & 4))
+            bwd_unrolled<0, LT, true>(spectrum + c, tiles + buf * WD_S * MC + s * MC + c, C,
+                                      reinterpret_cast<const float4*>(trig_all + (buf * WD_S + s) * WG_TRIG_STRIDE), acc);
+            const float ga = acc.ga(), gb = acc.gb(), gc = acc.gc();
+            float* gp = gp_all + (buf * COLS + t) * 3;
+            gp[0] = transpose ? -gc : ga;
+            gp[1] = transpose ? -gb : gb;
+            gp[2] = transpose ? -ga : gc;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + buf);       // release: the slice's tile and gp writes are visible to the producer
+        }
+    } else {
+        // ------------------------------------------------------------ producer warps (pw = 0, 1)
+        const int pw = warp - WD_MATH_WARPS, pl = pw * 32 + lane;       // pl = 0..63: lane of the producer pair
+        f32x2_t acc[KACC];
+#pragma unroll
+        for (int k = 0; k < KACC; ++k) acc[k] = 0ull;
+        // (sample, angle) pair pl (< 48) of a tile is this lane's trig job.  The angle of tile j + 1 is fetched while the
+        // table of tile j is computed, and the table is computed before the buffer is awaited: neither the DRAM latency
+        // nor sincosf sits between a buffer becoming free and its refill.
+        const bool trig_lane = pl < WD_S * 3;
+        const int t_ss = pl / 3, t_a = pl - 3 * t_ss;
+        auto load_phi = [&](int64_t j) -> float {      // angle of this lane's pair in the CTA's tile j (0 past the end)
+            if (!trig_lane || j >= my_tiles) return 0.f;
+            const int64_t n0 = (first + j * stride) * WD_S;
+            return transpose ? -__ldg(angles + (n0 + t_ss) * 3 + (2 - t_a)) : __ldg(angles + n0 * 3 + pl);
+        };
+        float tr[WG_TRIG_ANGLE];
+        auto trig_store = [&](int buf) {
+            if (trig_lane) {
+                float4* d = reinterpret_cast<float4*>(trig_all + (buf * WD_S + t_ss) * WG_TRIG_STRIDE + t_a * WG_TRIG_ANGLE);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) d[k] = make_float4(tr[4 * k], tr[4 * k + 1], tr[4 * k + 2], tr[4 * k + 3]);
+            }
+        };
+        auto issue_load = [&](int64_t j) {      // one lane: first arrival on full + the bulk load; L2 prefetch of the tile after it
+            const int buf = int(j) & (WD_BUFS - 1);
+            mbar_expect_tx(full + buf, TILE_BYTES);
+            tma_load(tiles + buf * WD_S * MC, gout + (first + j * stride) * WD_S * MC, TILE_BYTES, full + buf);
+            if (j + 1 < my_tiles)
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
+                             :: "l"(gout + (first + (j + 1) * stride) * WD_S * MC), "r"(TILE_BYTES) : "memory");
+        };
+        // prologue: fill the ring
+        float phi = load_phi(0);
+        for (int64_t j = 0; j < WD_BUFS && j < my_tiles; ++j) {
+            if (pl == 0) issue_load(j);
+            const float phi_next = load_phi(j + 1);
+            trig_fill(tr, phi);
+            trig_store(int(j));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full + int(j));
+            phi = phi_next;
+        }
+        // phi now belongs to tile min(WD_BUFS, my_tiles)
+        for (int64_t r = 0; r < my_tiles; ++r) {
+            const int buf = int(r) & (WD_BUFS - 1);
+            const int64_t jn = r + WD_BUFS;
+            if (jn < my_tiles) {
+                const float phi_next = load_phi(jn + 1);
+                trig_fill(tr, phi);
+                phi = phi_next;
+            }
+            mbar_wait(empty + buf, uint32_t(r >> 2) & 1u);
+            // batch reduction: column sums of the finished tile, float2 columns pl, pl + 64, ... (rows are 8-byte aligned)
+            const float* tile = tiles + buf * WD_S * MC;
+            if (!(WQ_ABLATE & 64)) {
+#pragma unroll
+                for (int row = 0; row < WD_S; ++row) {
+#pragma unroll
+                    for (int k = 0; k < KACC; ++k) {
+                        const int col2 = pl + 64 * k;
+                        if (col2 < NC2) {
+                            const float2 v = *reinterpret_cast<const float2*>(tile + row * MC + 2 * col2);
+                            asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc[k]) : "l"(wg2::pk(v.x, v.y)));
+                        }
+                    }
+                }
+            }
+            // angle gradients: sum the per-column parts over the channels
+            if (trig_lane) {
+                const int64_t n0 = (first + r * stride) * WD_S;
+                const float* gp = gp_all + buf * COLS * 3 + t_ss * C * 3 + t_a;
+                float sum = 0.f;
+#pragma unroll
+                for (int cc = 0; cc < C; ++cc) sum += gp[cc * 3];
+                gangles[n0 * 3 + pl] = sum;
+            }
+            if (jn < my_tiles) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy accesses of the buffer before the bulk write
+                named_bar_sync(1, 64);                                         // both producer warps are done with the buffer
+                if (pl == 0) issue_load(jn);
+                trig_store(buf);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full + buf);
+            }
+        }
+        float* prow = partial + int64_t(blockIdx.x) * MC;
+#pragma unroll
+        for (int k = 0; k < KACC; ++k) {
+            const int col2 = pl + 64 * k;
+            if (col2 < NC2) *reinterpret_cast<float2*>(prow + 2 * col2) = make_float2(wg2::plo(acc[k]), wg2::phi(acc[k]));
+        }
     }
 }
 
@@ -596,7 +761,7 @@ static int launch_bwd_tma(const WgGeom& g, const float* angles, const float* spe
     }
     const int64_t ntiles = N / WQ_S, n_full = ntiles * WQ_S, n_tail = N - n_full;
     const int grid = int(ntiles < g.sms ? ntiles : g.sms);
-    const size_t smem = size_t(WQ_BUFS * WQ_S * MC + WQ_GROUPS * WQ_S * WG_TRIG_STRIDE + WQ_GROUPS * WQ_GT * 3) * 4 + 2 * WQ_BUFS * 8;
+    const size_t smem = size_t(WQ_BUFS * WQ_S * MC + WQ_GROUPS * WQ_S * WG_TRIG_STRIDE + WQ_GROUPS * WQ_GT * 3 + (WQ_ITEM_SMEM ? MC : 0)) * 4 + 2 * WQ_BUFS * 8;
     int rc = opt_in_smem(wigner_bwd_tma_kernel<C, LT>, smem);
     if (rc) return rc;
     float* partial = workspace + int64_t(g.sms) * WQ_GROUPS * WQ_S * MC;
@@ -605,6 +770,37 @@ static int launch_bwd_tma(const WgGeom& g, const float* angles, const float* spe
     int rows = grid * WQ_GROUPS;
     if (n_tail > 0) {
         // ragged tail (< 16 samples): the cp.async kernel, one CTA, its partial row goes right after the others
+        WgGeom gt = g;
+        gt.ntiles = (n_tail + g.S - 1) / g.S;
+        int tail_grid = 0;
+        rc = launch_bwd<true, 0, -1>(gt, angles + n_full * 3, spectrum, gout + n_full * MC, gangles + n_full * 3, nullptr,
+                                     partial + int64_t(rows) * MC, int64_t(gt.ntiles) * MC, n_tail, 0, LT, C, transpose, st, &tail_grid);
+        if (rc) return rc;
+        rows += tail_grid;
+    }
+    wigner_reduce_partials<<<(MC + 31) / 32, dim3(32, 8), 0, st>>>(partial, gspectrum, rows, MC, accumulate);
+    return check_launch("wigner_reduce_partials");
+}
+
+template <int LT>
+static int launch_bwd_ws(const WgGeom& g, const float* angles, const float* spectrum, const float* gout, float* gangles,
+                         float* gspectrum, float* workspace, int64_t workspace_floats, int64_t N, int transpose, int accumulate,
+                         cudaStream_t st) {
+    constexpr int C = 10, MC = (LT + 1) * (LT + 1) * C;
+    if (!workspace || workspace_floats < tma_bwd_workspace_rows(g.sms) * MC) {
+        set_error("wigner_apply_bwd: workspace of %lld floats required", (long long)(tma_bwd_workspace_rows(g.sms) * MC));
+        return LV_ERR_ARG;
+    }
+    const int64_t ntiles = N / WD_S, n_full = ntiles * WD_S, n_tail = N - n_full;
+    const int grid = int(ntiles < g.sms ? ntiles : g.sms);
+    const size_t smem = size_t(WD_BUFS * WD_S * MC + WD_BUFS * WD_S * WG_TRIG_STRIDE + WD_BUFS * WD_S * C * 3) * 4 + 2 * WD_BUFS * 8 + 16;
+    int rc = opt_in_smem(wigner_bwd_ws_kernel<C, LT>, smem);
+    if (rc) return rc;
+    float* partial = workspace;      // one row per CTA, then the tail's rows
+    wigner_bwd_ws_kernel<C, LT><<<grid, WD_THREADS, smem, st>>>(angles, spectrum, gout, gangles, partial, ntiles, transpose);
+    if ((rc = check_launch("wigner_apply_bwd (ws)"))) return rc;
+    int rows = grid;
+    if (n_tail > 0) {
         WgGeom gt = g;
         gt.ntiles = (n_tail + g.S - 1) / g.S;
         int tail_grid = 0;
@@ -671,8 +867,13 @@ extern "C" int lv_wigner_apply_bwd_f32(const float* angles, const float* spectru
     if (!angles || !spectrum || !gout || !gangles) { lv::set_error("wigner_apply_bwd: null pointer"); return LV_ERR_ARG; }
     int grid = 0;
     if (shared_spectrum && lv::tma_bwd_eligible(C, lmin, lmax, gout, N)) {
+#if WQ_USE_GROUPS
         if (lmax == 8) return lv::launch_bwd_tma<8>(g, angles, spectrum, gout, gangles, gspectrum, workspace, workspace_floats, N, transpose, accumulate, st);
         return lv::launch_bwd_tma<6>(g, angles, spectrum, gout, gangles, gspectrum, workspace, workspace_floats, N, transpose, accumulate, st);
+#else
+        if (lmax == 8) return lv::launch_bwd_ws<8>(g, angles, spectrum, gout, gangles, gspectrum, workspace, workspace_floats, N, transpose, accumulate, st);
+        return lv::launch_bwd_ws<6>(g, angles, spectrum, gout, gangles, gspectrum, workspace, workspace_floats, N, transpose, accumulate, st);
+#endif
     }
     if (shared_spectrum) {
         rc = WG_DISPATCH(C, lmin, lmax, true, lv::launch_bwd, g, angles, spectrum, gout, gangles, gspectrum, workspace, workspace_floats, N, lmin, lmax, C, transpose, st, &grid);
