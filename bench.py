@@ -343,11 +343,11 @@ def run_ours(args):
                     "h2d_bytes_per_step": n_loc * 60, "d2h_bytes_per_step": 4 * (1 + M * CHANNELS),
                     "api": "so3_reparameterize_eazyz -> WignerApply (torch.autograd), pinned host mu/sigma/eps, double-buffered copies"},
             "gpu_launches": (step_obj.LAUNCHES_PER_MICROBATCH * n_micro + step_obj.LAUNCHES_PER_SHARD) * args.steps,
-            "roofline": {"bound": "hbm", "kernel": "wigner_bwd_tma_kernel<10,8> (+ row-reduction kernels)", "achieved": kernels[dom]["gbs"], "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "wigner_bwd_ws_kernel<10,8> (+ wigner_reduce_partials)", "achieved": kernels[dom]["gbs"], "peak": peak,
                          "unit": "GB/s", "frac": kernels[dom]["frac"],
                          # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture
-                         # profiles/r01_ncu_wigner_v3_summary.txt (852.56 MB + 8.06 MB at 2^18 samples per launch)
-                         "traffic": 860.62e6 * (micro / 262144.0), "peak_source": peak_src,
+                         # profiles/r01_ncu_wigner_v4_summary.txt (852.56 MB + 7.75 MB at 2^18 samples per launch)
+                         "traffic": 860.31e6 * (micro / 262144.0), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": abytes[dom] * micro},
             "pipeline_roofline": {"bytes_per_sample": 6656, "achieved_gbs": round(value / world * 6656 / 1e9, 1),
                                   "frac": round(value / world * 6656 / 1e9 / peak, 4)},

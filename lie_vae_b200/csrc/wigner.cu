@@ -7,20 +7,23 @@
 // left on the vector:
 //      y_l = X(a) ( J ( X(b) ( J ( X(c) s_l ) ) ) )
 // X(phi) is a set of independent 2x2 rotations of the pairs (i, 2l-i) by (l-i)*phi, and J_l is
-// ~25% dense with compile-time coefficients (wigner_gen.cuh, one immediate-operand FMA per
-// non-zero).  One thread owns one (sample, channel) column; the degree-l vector (<= 17 floats)
-// lives in registers.  cos/sin(m*angle), m = 1..8, are computed once per sample by three threads
-// (sincosf + angle-addition recurrence) and shared through smem.
+// ~25% dense with compile-time coefficients.  One thread owns one (sample, channel) column; the
+// degree-l vector (<= 17 floats) lives in registers, packed pairwise so that every operator of the
+// chain is issued as two-wide FP32 instructions (fma/mul.rn.f32x2 -> SASS FFMA2/FMUL2; layout and
+// code in the generated wigner_gen.cuh): the kernels are bound by FP32 instruction issue / the FMA
+// pipe, not by memory.  cos/sin(m*angle), m = 1..8, are computed once per sample (sincosf +
+// angle-addition recurrence) and shared through smem in the pairing order of the packed operators.
 //
 // Data movement (Blackwell): the CTA's (S, M, C) tile is one contiguous span of HBM.
 //   forward : columns are assembled in shared memory and the whole tile leaves with ONE TMA bulk
 //             store (cp.async.bulk.global.shared::cta) issued by one thread -- no per-thread
 //             copy-out loop, the LSU and the issue slots stay with the math;
-//   backward: (shared spectrum, the ActionNet case) one persistent CTA per SM, three math groups, four
-//             tile buffers fed by TMA bulk loads on mbarriers; finished tiles are summed over the batch by
-//             TMA bulk reduce-adds into fp32 accumulators in global memory -- see wigner_bwd_tma_kernel.
-//             (per-sample spectrum, other C / degree ranges, ragged tails: wigner_bwd_kernel, where the
-//             tile lands by cp.async and the spectrum gradient overwrites it in place.)
+//   backward: (shared spectrum, the ActionNet case) one persistent CTA per SM: math warps pull
+//             32-column slices of TMA-loaded tiles from a work counter, two producer warps recycle
+//             the four tile buffers (column-sum batch reduction, TMA refill, trig tables) -- see
+//             wigner_bwd_ws_kernel.  (per-sample spectrum, other C / degree ranges, ragged tails:
+//             wigner_bwd_kernel, where the tile lands by cp.async and the spectrum gradient
+//             overwrites it in place.)
 // Specialisations: the channel count (10, the ActionNet default) and the degree range (0..8 and
 // 0..6) are template parameters for the common cases, so the degree loop is fully unrolled and every
 // tile / spectrum access is base + immediate; <CT = 0, LT = -1> is the run-time fallback for
@@ -32,14 +35,14 @@
 //      g_a = <h4, G w4>,  g_b = <h2, G w2>,  g_c = <g_s, G s>,   w2 = J X(c) s, w4 = J X(b) w2
 // so only w2 and w4 are recomputed from the spectrum; nothing is saved by the forward.
 // For a shared spectrum (ActionNet.item_rep, decoders.py:53) the per-sample g_s are summed over
-// the batch reproducibly: every accumulator element receives its per-tile contributions in tile
-// order (TMA kernel: one bulk reduce-add per tile and group; cp.async kernel: per-CTA smem
-// accumulator), then one partial row per group / CTA -> a second tiny kernel.  No SM-side atomics.
+// the batch reproducibly: tiles are assigned to CTAs statically and every CTA adds its tiles' rows
+// in a fixed order (warp-decoupled kernel: the producer warps' register accumulators; cp.async
+// kernel: per-CTA smem accumulator), then one partial row per CTA -> a second tiny kernel.  No atomics.
 //
 // transpose=True (lie_tools.py:249-250): D^T = X(-c) J X(-b) J X(-a), i.e. the same kernels on
 // the angles (-c, -b, -a), with the angle gradients mapped back.
 #include "common.cuh"
-#include "wigner_gen2.cuh"
+#include "wigner_gen.cuh"
 
 namespace lv {
 
@@ -52,7 +55,7 @@ using wg2::PDeg;
 using wg2::f32x2_t;
 
 // Per-sample trig table: 3 angles x 4 float4 slots; slot q of an angle holds (cos m1 phi, cos m2 phi, sin m1 phi, sin m2 phi)
-// for the frequency pairs (1,3) (5,7) (2,4) (6,8) -- the pairing of wigner_gen2.cuh, so that a pair rotation
+// for the frequency pairs (1,3) (5,7) (2,4) (6,8) -- the pairing of wigner_gen.cuh, so that a pair rotation
 // (lie_tools.py:195-208: X[i,i] = cos((l-i)phi), X[i,2l-i] = sin((l-i)phi)) reads its operands with one LDS.128.
 constexpr int WG_TRIG_ANGLE = 16;   // floats per angle
 __device__ __forceinline__ int trig_index(int m) {      // float offset of cos(m phi) inside an angle's block; sin is +2
@@ -317,32 +320,7 @@ wigner_bwd_kernel(const float* __restrict__ angles, const float* __restrict__ sp
         for (int o = t; o < MC; o += blockDim.x) partial[int64_t(blockIdx.x) * MC + o] = s_acc[o];
 }
 
-// ------------------------------------------------------------------ backward, shared spectrum, TMA-fed (sm_100a)
-// One persistent CTA per SM with three math groups of 160 threads and four 16-sample tile buffers.  Tile j of the CTA
-// lives in buffer j % 4 and is processed by group j % 3.  A group that has finished a tile hands it to the copy engine
-// twice: a TMA bulk reduce-add (cp.reduce.async.bulk ... add.f32; the group's first tile is a plain bulk store) of the
-// gradient rows into the group's own fp32 accumulator in global memory, then a TMA bulk load of tile j + 4 into the same
-// buffer, completing on the buffer's mbarrier.  Three tiles are always being computed while the fourth is in flight, so
-// the math groups never execute a copy loop or a reduction loop and never wait for HBM in steady state.  Each accumulator
-// element receives exactly one add per tile, in tile order: the batch sum stays run-to-run reproducible.
-// Requires full 16-sample tiles and 16-byte aligned g_y (the host sends a ragged tail through wigner_bwd_kernel).
-#ifndef WQ_GROUPS_N
-#define WQ_GROUPS_N 3
-#endif
-#ifndef WQ_ITEM_SMEM
-#define WQ_ITEM_SMEM 0
-#endif
-#ifndef WQ_USE_GROUPS      // 1: the group-barrier kernel (wigner_bwd_tma_kernel); 0: the warp-decoupled kernel
-#define WQ_USE_GROUPS 0
-#endif
-#ifndef WQ_L2_PREFETCH     // tiles ahead of the TMA load that are prefetched into L2 (0 = off)
-#define WQ_L2_PREFETCH 0
-#endif
-#ifndef WQ_ABLATE          // experiments only (tools/exp/variant.py): 1 no reduce-add, 2 plain store instead, 4 no math
-#define WQ_ABLATE 0
-#endif
-constexpr int WQ_S = 16, WQ_GROUPS = WQ_GROUPS_N, WQ_BUFS = 4, WQ_GT = 160, WQ_THREADS = WQ_GROUPS * WQ_GT;
-
+// ------------------------------------------------------------------ mbarrier / TMA helpers (sm_100a)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory"); }
@@ -356,120 +334,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void tma_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-
-template <int CT, int LT>
-__global__ void __launch_bounds__(WQ_THREADS, 1)
-wigner_bwd_tma_kernel(const float* __restrict__ angles, const float* __restrict__ spectrum, const float* __restrict__ gout,
-                      float* __restrict__ gangles, float* __restrict__ gacc, float* __restrict__ partial, int64_t ntiles,
-                      int transpose) {
-    constexpr int C = CT, M = (LT + 1) * (LT + 1), MC = M * C;
-    constexpr uint32_t TILE_BYTES = WQ_S * MC * 4u;
-    extern __shared__ __align__(16) float smem[];
-    float* tiles = smem;                                          // [4][16][MC]
-    float* trig_all = tiles + WQ_BUFS * WQ_S * MC;                 // [3][16][52]
-    float* gp_all = trig_all + WQ_GROUPS * WQ_S * WG_TRIG_STRIDE;  // [3][160][3]
-    // full[buf][use & 1]: two mbarriers per buffer, alternating between consecutive uses of the buffer.  With a single
-    // barrier per buffer a group that runs two uses ahead of a starved group would see the 1-bit phase parity of the
-    // previous use and walk into a buffer that is still being computed on.
-    uint64_t* full = reinterpret_cast<uint64_t*>(gp_all + WQ_GROUPS * WQ_GT * 3);   // [4][2]
-    float* s_item = reinterpret_cast<float*>(full + 2 * WQ_BUFS);                   // [MC] (WQ_ITEM_SMEM)
-    const int tid = threadIdx.x, g = tid / WQ_GT, t = tid - g * WQ_GT;
-    const int s = t / C, c = t - s * C;
-    float* s_trig = trig_all + g * WQ_S * WG_TRIG_STRIDE;
-    float* s_gp = gp_all + g * WQ_GT * 3;
-    // tiles of this CTA: blockIdx.x + j * gridDim.x, j = 0, 1, ...
-    const int64_t first = blockIdx.x, stride = gridDim.x;
-    const int64_t my_tiles = first < ntiles ? (ntiles - first + stride - 1) / stride : 0;
-    float* acc = gacc + (int64_t(blockIdx.x) * WQ_GROUPS + g) * WQ_S * MC;
-    if (tid == 0) {
-        for (int b = 0; b < 2 * WQ_BUFS; ++b) mbar_init(full + b, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (WQ_ITEM_SMEM) for (int o = tid; o < MC; o += WQ_THREADS) s_item[o] = __ldg(spectrum + o);
-    __syncthreads();
-    if (tid == 0) {
-        for (int j = 0; j < WQ_BUFS && j < my_tiles; ++j) {
-            mbar_expect_tx(full + 2 * j, TILE_BYTES);          // use 0 of buffer j
-            tma_load(tiles + j * WQ_S * MC, gout + (first + j * stride) * WQ_S * MC, TILE_BYTES, full + 2 * j);
-        }
-    }
-    for (int64_t j = g; j < my_tiles; j += WQ_GROUPS) {
-        const int buf = int(j % WQ_BUFS);
-        const int64_t use = j / WQ_BUFS;                       // how often this buffer has been filled before
-        uint64_t* bar = full + 2 * buf + int(use & 1);
-        const uint32_t parity = uint32_t(use >> 1) & 1u;
-        const int64_t n0 = (first + j * stride) * WQ_S;
-        float* tile = tiles + buf * WQ_S * MC;
-        // trig table of this tile (group-private), then wait for the tile itself
-        for (int q = t; q < WQ_S * 3; q += WQ_GT) {
-            const int ss = q / 3, a = q - 3 * ss;
-            const float phi = transpose ? -__ldg(angles + (n0 + ss) * 3 + (2 - a)) : __ldg(angles + n0 * 3 + q);
-            trig_fill(s_trig + ss * WG_TRIG_STRIDE + a * WG_TRIG_ANGLE, phi);
-        }
-        if (!(WQ_ABLATE & 32)) mbar_wait(bar, parity);
-        if (!(WQ_ABLATE & 16)) named_bar_sync(1 + g, WQ_GT);
-        if (!(WQ_ABLATE & 4)) {
-            AngleAcc acc;
-            bwd_unrolled<0, LT, !WQ_ITEM_SMEM>((WQ_ITEM_SMEM ? s_item : spectrum) + c, tile + s * MC + c, C, reinterpret_cast<const float4*>(s_trig + s * WG_TRIG_STRIDE), acc);
-            const float ga = acc.ga(), gb = acc.gb(), gc = acc.gc();
-            s_gp[t * 3 + 0] = transpose ? -gc : ga;
-            s_gp[t * 3 + 1] = transpose ? -gb : gb;
-            s_gp[t * 3 + 2] = transpose ? -ga : gc;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy tile writes -> visible to the copy engine
-        if (!(WQ_ABLATE & 8)) named_bar_sync(1 + g, WQ_GT);
-        if (t == WQ_GT - 1) {      // a lane that neither builds the trig table nor sums the angle gradients
-            if (WQ_ABLATE & 1) {
-            } else if (j == g || (WQ_ABLATE & 2))
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                             :: "l"(acc), "r"(smem_u32(tile)), "r"(TILE_BYTES) : "memory");
-            else
-                asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
-                             :: "l"(acc), "r"(smem_u32(tile)), "r"(TILE_BYTES) : "memory");
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            if (j == g)     // the initialising store must have landed before the first reduce-add is issued (bulk ops are unordered)
-                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-            else
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the engine has read the buffer: refill it
-            const int64_t jn = j + WQ_BUFS;
-            if (jn < my_tiles && !(WQ_ABLATE & 32)) {
-                uint64_t* nbar = full + 2 * buf + int((use + 1) & 1);
-                mbar_expect_tx(nbar, TILE_BYTES);
-                tma_load(tile, gout + (first + jn * stride) * WQ_S * MC, TILE_BYTES, nbar);
-            }
-            if (WQ_L2_PREFETCH > 0 && jn + WQ_L2_PREFETCH < my_tiles)
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
-                             :: "l"(gout + (first + (jn + WQ_L2_PREFETCH) * stride) * WQ_S * MC), "r"(TILE_BYTES) : "memory");
-        }
-        for (int q = t; q < WQ_S * 3; q += WQ_GT) {
-            const int ss = q / 3, a = q - 3 * ss;
-            float sum = 0.f;
-#pragma unroll
-            for (int cc = 0; cc < C; ++cc) sum += s_gp[(ss * C + cc) * 3 + a];
-            gangles[n0 * 3 + q] = sum;
-        }
-    }
-    // The group's 16-row accumulator -> one partial row.  The issuing lane waits until all of its bulk reductions have
-    // been performed, orders the async-proxy writes before the generic-proxy reads below, and the group barrier hands
-    // that ordering to the other lanes; the reads bypass L1 (the SM never cached these lines).
-    if (t == WQ_GT - 1) {
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-        asm volatile("fence.proxy.async;" ::: "memory");
-        __threadfence();
-    }
-    named_bar_sync(1 + g, WQ_GT);
-    float* prow = partial + (int64_t(blockIdx.x) * WQ_GROUPS + g) * MC;
-    if (g < my_tiles) {
-        for (int o = t; o < MC; o += WQ_GT) {
-            float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-            for (int r = 0; r < WQ_S; r += 2) { a0 += __ldcg(acc + r * MC + o); a1 += __ldcg(acc + (r + 1) * MC + o); }
-            prow[o] = a0 + a1;
-        }
-    } else {
-        for (int o = t; o < MC; o += WQ_GT) prow[o] = 0.f;      // a group without work contributes a zero row
-    }
 }
 
 // ------------------------------------------------------------------ backward, shared spectrum, warp-decoupled (sm_100a)
@@ -487,10 +351,8 @@ wigner_bwd_tma_kernel(const float* __restrict__ angles, const float* __restrict_
 //     L2 prefetch of the tile after it) -> write the trig table of tile r + 4, which it computed *before* the wait ->
 //     arrive on full.  The buffer's turnaround is column sums + one load latency; three tiles are being computed meanwhile.
 // Requires full 16-sample tiles and 16-byte aligned g_y (the host sends a ragged tail through wigner_bwd_kernel).
-#ifndef WD_MATH_WARPS_N
-#define WD_MATH_WARPS_N 14
-#endif
-constexpr int WD_S = 16, WD_BUFS = 4, WD_MATH_WARPS = WD_MATH_WARPS_N, WD_THREADS = (WD_MATH_WARPS + 2) * 32, WD_SLICES = 5;
+// 14 math warps + 2 producer warps = 16 warps x 128 registers: the whole register file (warps are allocated in fours)
+constexpr int WD_S = 16, WD_BUFS = 4, WD_MATH_WARPS = 14, WD_THREADS = (WD_MATH_WARPS + 2) * 32, WD_SLICES = 5;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
@@ -535,7 +397,6 @@ wigner_bwd_ws_kernel(const float* __restrict__ angles, const float* __restrict__
             const int t = p * 32 + lane, s = t / C, c = t - s * C;
             mbar_wait(full + buf, uint32_t(q >> 2) & 1u);
             AngleAcc acc;
-            if (!(WQ_ABLATE & 4))
             bwd_unrolled<0, LT, true>(spectrum + c, tiles + buf * WD_S * MC + s * MC + c, C,
                                       reinterpret_cast<const float4*>(trig_all + (buf * WD_S + s) * WG_TRIG_STRIDE), acc);
             const float ga = acc.ga(), gb = acc.gb(), gc = acc.gc();
@@ -601,7 +462,7 @@ wigner_bwd_ws_kernel(const float* __restrict__ angles, const float* __restrict__
             mbar_wait(empty + buf, uint32_t(r >> 2) & 1u);
             // batch reduction: column sums of the finished tile, float2 columns pl, pl + 64, ... (rows are 8-byte aligned)
             const float* tile = tiles + buf * WD_S * MC;
-            if (!(WQ_ABLATE & 64)) {
+            {
 #pragma unroll
                 for (int row = 0; row < WD_S; ++row) {
 #pragma unroll
@@ -742,53 +603,21 @@ static int launch_bwd(const WgGeom& g, const float* angles, const float* spectru
     return check_launch("wigner_apply_bwd");
 }
 
-// ---- TMA-fed backward (shared spectrum, C = 10, degrees 0..8 or 0..6, 16-byte aligned g_y) -------------------------
+// ---- warp-decoupled backward (shared spectrum, C = 10, degrees 0..8 or 0..6, 16-byte aligned g_y) -----------------
 
-static bool tma_bwd_eligible(int C, int lmin, int lmax, const float* gout, int64_t N) {
-    return C == 10 && lmin == 0 && (lmax == 8 || lmax == 6) && N >= WQ_S && (reinterpret_cast<uintptr_t>(gout) & 15u) == 0;
+static bool ws_bwd_eligible(int C, int lmin, int lmax, const float* gout, int64_t N) {
+    return C == 10 && lmin == 0 && (lmax == 8 || lmax == 6) && N >= WD_S && (reinterpret_cast<uintptr_t>(gout) & 15u) == 0;
 }
-// workspace rows (of MC floats): accumulators [sms*3*16] | one partial row per (CTA, group) [sms*3] | tail partial [1]
-static int64_t tma_bwd_workspace_rows(int sms) { return int64_t(sms) * WQ_GROUPS * (WQ_S + 1) + 1; }
-
-template <int LT>
-static int launch_bwd_tma(const WgGeom& g, const float* angles, const float* spectrum, const float* gout, float* gangles,
-                          float* gspectrum, float* workspace, int64_t workspace_floats, int64_t N, int transpose, int accumulate,
-                          cudaStream_t st) {
-    constexpr int C = 10, MC = (LT + 1) * (LT + 1) * C;
-    if (!workspace || workspace_floats < tma_bwd_workspace_rows(g.sms) * MC) {
-        set_error("wigner_apply_bwd: workspace of %lld floats required", (long long)(tma_bwd_workspace_rows(g.sms) * MC));
-        return LV_ERR_ARG;
-    }
-    const int64_t ntiles = N / WQ_S, n_full = ntiles * WQ_S, n_tail = N - n_full;
-    const int grid = int(ntiles < g.sms ? ntiles : g.sms);
-    const size_t smem = size_t(WQ_BUFS * WQ_S * MC + WQ_GROUPS * WQ_S * WG_TRIG_STRIDE + WQ_GROUPS * WQ_GT * 3 + (WQ_ITEM_SMEM ? MC : 0)) * 4 + 2 * WQ_BUFS * 8;
-    int rc = opt_in_smem(wigner_bwd_tma_kernel<C, LT>, smem);
-    if (rc) return rc;
-    float* partial = workspace + int64_t(g.sms) * WQ_GROUPS * WQ_S * MC;
-    wigner_bwd_tma_kernel<C, LT><<<grid, WQ_THREADS, smem, st>>>(angles, spectrum, gout, gangles, workspace, partial, ntiles, transpose);
-    if ((rc = check_launch("wigner_apply_bwd (tma)"))) return rc;
-    int rows = grid * WQ_GROUPS;
-    if (n_tail > 0) {
-        // ragged tail (< 16 samples): the cp.async kernel, one CTA, its partial row goes right after the others
-        WgGeom gt = g;
-        gt.ntiles = (n_tail + g.S - 1) / g.S;
-        int tail_grid = 0;
-        rc = launch_bwd<true, 0, -1>(gt, angles + n_full * 3, spectrum, gout + n_full * MC, gangles + n_full * 3, nullptr,
-                                     partial + int64_t(rows) * MC, int64_t(gt.ntiles) * MC, n_tail, 0, LT, C, transpose, st, &tail_grid);
-        if (rc) return rc;
-        rows += tail_grid;
-    }
-    wigner_reduce_partials<<<(MC + 31) / 32, dim3(32, 8), 0, st>>>(partial, gspectrum, rows, MC, accumulate);
-    return check_launch("wigner_reduce_partials");
-}
+// workspace rows (of MC floats): one partial row per CTA [sms] | tail partial [1]
+static int64_t ws_bwd_workspace_rows(int sms) { return int64_t(sms) + 1; }
 
 template <int LT>
 static int launch_bwd_ws(const WgGeom& g, const float* angles, const float* spectrum, const float* gout, float* gangles,
                          float* gspectrum, float* workspace, int64_t workspace_floats, int64_t N, int transpose, int accumulate,
                          cudaStream_t st) {
     constexpr int C = 10, MC = (LT + 1) * (LT + 1) * C;
-    if (!workspace || workspace_floats < tma_bwd_workspace_rows(g.sms) * MC) {
-        set_error("wigner_apply_bwd: workspace of %lld floats required", (long long)(tma_bwd_workspace_rows(g.sms) * MC));
+    if (!workspace || workspace_floats < ws_bwd_workspace_rows(g.sms) * MC) {
+        set_error("wigner_apply_bwd: workspace of %lld floats required", (long long)(ws_bwd_workspace_rows(g.sms) * MC));
         return LV_ERR_ARG;
     }
     const int64_t ntiles = N / WD_S, n_full = ntiles * WD_S, n_tail = N - n_full;
@@ -828,8 +657,8 @@ extern "C" int64_t lv_wigner_bwd_workspace_floats(int64_t N, int lmin, int lmax,
     if (lv::wigner_geometry("wigner_bwd_workspace", N, lmin, lmax, C, true, g) != LV_OK) return -1;
     const int64_t cap = int64_t(g.sms) * lv::WG_MAX_CTAS_PER_SM;
     int64_t rows = g.ntiles < cap ? g.ntiles : cap;
-    if (C == 10 && lmin == 0 && (lmax == 8 || lmax == 6) && N >= lv::WQ_S) {
-        const int64_t tma_rows = lv::tma_bwd_workspace_rows(g.sms);
+    if (C == 10 && lmin == 0 && (lmax == 8 || lmax == 6) && N >= lv::WD_S) {
+        const int64_t tma_rows = lv::ws_bwd_workspace_rows(g.sms);
         if (tma_rows > rows) rows = tma_rows;
     }
     return rows * g.MC;
@@ -866,14 +695,9 @@ extern "C" int lv_wigner_apply_bwd_f32(const float* angles, const float* spectru
     }
     if (!angles || !spectrum || !gout || !gangles) { lv::set_error("wigner_apply_bwd: null pointer"); return LV_ERR_ARG; }
     int grid = 0;
-    if (shared_spectrum && lv::tma_bwd_eligible(C, lmin, lmax, gout, N)) {
-#if WQ_USE_GROUPS
-        if (lmax == 8) return lv::launch_bwd_tma<8>(g, angles, spectrum, gout, gangles, gspectrum, workspace, workspace_floats, N, transpose, accumulate, st);
-        return lv::launch_bwd_tma<6>(g, angles, spectrum, gout, gangles, gspectrum, workspace, workspace_floats, N, transpose, accumulate, st);
-#else
+    if (shared_spectrum && lv::ws_bwd_eligible(C, lmin, lmax, gout, N)) {
         if (lmax == 8) return lv::launch_bwd_ws<8>(g, angles, spectrum, gout, gangles, gspectrum, workspace, workspace_floats, N, transpose, accumulate, st);
         return lv::launch_bwd_ws<6>(g, angles, spectrum, gout, gangles, gspectrum, workspace, workspace_floats, N, transpose, accumulate, st);
-#endif
     }
     if (shared_spectrum) {
         rc = WG_DISPATCH(C, lmin, lmax, true, lv::launch_bwd, g, angles, spectrum, gout, gangles, gspectrum, workspace, workspace_floats, N, lmin, lmax, C, transpose, st, &grid);

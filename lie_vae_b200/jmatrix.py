@@ -21,7 +21,7 @@ system in float64, then zeroing entries below 1e-12.  Known closed forms
 
 Nothing here touches the GPU; the table is uploaded once through
 ``lv_wigner_set_j`` for the generic kernels and baked into
-``csrc/wigner_gen.cuh`` by ``tools/gen_wigner.py`` for the unrolled ones.
+``csrc/wigner_gen.cuh`` by ``tools/gen_wigner.py`` for the unrolled, packed ones.
 """
 from functools import lru_cache
 import math

@@ -43,7 +43,7 @@ class FusedSO3ActionStep:
     is 3.2 kB/sample, is micro-batched so that y / g_y never need to be resident for the full shard.
     """
 
-    LAUNCHES_PER_MICROBATCH = 3      # wigner fwd, wigner bwd (TMA-fed), wigner_reduce_partials
+    LAUNCHES_PER_MICROBATCH = 3      # wigner fwd, wigner bwd (warp-decoupled, TMA-fed), wigner_reduce_partials
     LAUNCHES_PER_SHARD = 2           # latent fwd, latent bwd
 
     def __init__(self, shard, micro, degrees=8, rep_copies=10, k=3, transpose=False, device="cuda"):

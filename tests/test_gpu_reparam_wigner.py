@@ -296,8 +296,8 @@ def test_wigner_errors(mods):
 @pytest.mark.parametrize("L", [8, 6])
 @pytest.mark.parametrize("N", [16, 17, 31, 48, 49, 16 * 150 + 3, 16 * 600])
 @pytest.mark.parametrize("tr", [False, True])
-def test_tma_backward_matches_cp_async_backward(mods, L, N, tr):
-    """The TMA-fed backward (C = 10, degrees 0..8 / 0..6, 16-byte aligned g_y) against the cp.async kernel, which
+def test_ws_backward_matches_cp_async_backward(mods, L, N, tr):
+    """The warp-decoupled TMA-fed backward (C = 10, degrees 0..8 / 0..6, 16-byte aligned g_y) against the cp.async kernel, which
     the same call falls back to when g_y is only 4-byte aligned; and against the oracle for the small sizes."""
     from lie_vae_b200 import _ops
     torch.manual_seed(N + L)
@@ -328,10 +328,10 @@ def test_tma_backward_matches_cp_async_backward(mods, L, N, tr):
         close(ga1, a64.grad, 2e-5, 1e-4)
 
 
-def test_tma_backward_stress_reproducible(mods):
-    """Many back-to-back launches of the TMA-fed backward (persistent CTAs, 4 mbarrier-tracked tile buffers per SM):
-    every launch must reproduce the first one bit for bit.  Guards the buffer hand-over protocol (a single barrier per
-    buffer aliased its 1-bit phase when one math group was starved; that showed up as a rare launch failure)."""
+def test_ws_backward_stress_reproducible(mods):
+    """Many back-to-back launches of the warp-decoupled backward (persistent CTAs, math warps pulling slices from a work
+    counter, producer warps recycling 4 mbarrier-tracked tile buffers per SM): every launch must reproduce the first one
+    bit for bit, whichever warp computed which slice.  Guards the full/empty hand-over protocol."""
     from lie_vae_b200 import _ops
     torch.manual_seed(5)
     N, L, C = 1 << 17, 8, 10

@@ -1,6 +1,6 @@
 // Experimental Wigner forward variants for ablation timing (NOT product code; built by tools/exp/run_exp.py).
 #include "../../lie_vae_b200/csrc/common.cuh"
-#include "../../lie_vae_b200/csrc/wigner_gen.cuh"
+#include "wigner_gen_scalar.cuh"
 #include <cstdio>
 
 namespace lv {

@@ -1,12 +1,22 @@
 #!/usr/bin/env python
-"""Generate lie_vae_b200/csrc/wigner_gen.cuh: fully unrolled sparse J_l multiplies.
+"""Generate lie_vae_b200/csrc/wigner_gen.cuh: per-degree Wigner chain operators in packed f32x2 form.
 
-The Pinchon-Hoggan matrices J_l (regenerated analytically by
-lie_vae_b200/jmatrix.py; the reference loads them from lie_learn,
-lie_tools.py:10-14) are ~25% dense.  Emitting one explicit FMA per non-zero, with
-the coefficient as an immediate operand, is what makes the Wigner apply kernels
-affordable on the FP32 pipe: 247 multiply-adds for all degrees l <= 8 instead of
-969 for dense blocks, no loads, no index arithmetic.
+Blackwell (sm_100a) has two-wide FP32 instructions (PTX fma/mul.rn.f32x2, SASS FFMA2 / FMUL2) that do two
+independent FMAs per issue slot on an aligned register pair.  The FP32 pipe does not get faster, but the
+Wigner kernels are *issue* bound, so halving the number of FP instructions is what counts.  Instead of
+giving a thread two channels (twice the registers, measured slower), the 2l+1 entries of ONE column are
+packed pairwise so that every operator of the chain  X(a) J X(b) J X(c)  works on whole pairs:
+
+  * entries are addressed by frequency m: lo_m = x[l-m], hi_m = x[l+m], centre x[l];
+  * frequencies of equal parity are paired: (1,3) (5,7) | (2,4) (6,8); a class with an odd count leaves one
+    frequency unpaired ("single"), which stays scalar;
+  * X(phi) rotates (lo_m, hi_m) by m*phi: on a pair of frequencies that is 2 FMUL2 + 2 FFMA2 with the
+    (cos, cos) and (sin, sin) pairs read from the trig table (negations fold into operand modifiers);
+  * J_l (Pinchon-Hoggan, ~25 % dense) is block structured by exactly these classes (rows lo/even, lo/odd,
+    hi/odd, centre+hi/even each read one class), so two paired output rows share their input columns:
+    (y_r1, y_r2) += (J[r1,c], J[r2,c]) * broadcast(x_c) is ONE FFMA2 whose coefficient pair comes from
+    constant memory through a uniform register pair and whose x operand is a scalar-broadcast register;
+  * the generator products <h, G w> pair the same way.
 
 Usage:  python tools/gen_wigner.py [LMAX]      (default 8)
 """
@@ -21,67 +31,197 @@ spec.loader.exec_module(jm)
 
 
 def lit(v):
-    return "%.9gf" % v if ("." in "%.9g" % v or "e" in "%.9g" % v) else "%.9g.0f" % v
+    s = "%.9g" % v
+    return s + "f" if ("." in s or "e" in s) else s + ".0f"
 
 
-def emit_jmul(l):
+def layout(l):
+    """pair slots [(m1, m2)], single frequencies [m], and their trig-table positions."""
+    odd = list(range(1, l + 1, 2))
+    even = list(range(2, l + 1, 2))
+    pairs, singles = [], []
+    for cls in (odd, even):
+        for i in range(0, len(cls) - 1, 2):
+            pairs.append((cls[i], cls[i + 1]))
+        if len(cls) % 2:
+            singles.append(cls[-1])
+    return pairs, singles
+
+
+def trig_pos(m):
+    """(float4 slot, lane) of frequency m in the per-angle trig table [(c_m1, c_m2, s_m1, s_m2)] x 4."""
+    if m % 2:
+        return (m - 1) // 4, ((m - 1) // 2) % 2
+    return 2 + (m - 2) // 4, ((m - 2) // 2) % 2
+
+
+class Deg:
+    def __init__(self, l):
+        self.l = l
+        self.pairs, self.singles = layout(l)
+        self.where = {}          # element index -> accessor expression template with '{v}'
+        for q, (m1, m2) in enumerate(self.pairs):
+            self.where[l - m1] = "plo({v}.lo[%d])" % q
+            self.where[l - m2] = "phi({v}.lo[%d])" % q
+            self.where[l + m1] = "plo({v}.hi[%d])" % q
+            self.where[l + m2] = "phi({v}.hi[%d])" % q
+        for s, m in enumerate(self.singles):
+            self.where[l - m] = "{v}.slo[%d]" % s
+            self.where[l + m] = "{v}.shi[%d]" % s
+        self.where[l] = "{v}.ctr"
+
+    def acc(self, i, v):
+        return self.where[i].format(v=v)
+
+
+def emit(l, ktab):
+    d = Deg(l)
     J = jm.j_matrix_np(l)
-    d = 2 * l + 1
-    lines = ["template <> struct JMul<%d> {" % l,
-             "template <typename V> static __device__ __forceinline__ void mul(const V (&x)[%d], V (&y)[%d]) {" % (d, d)]
-    nnz = 0
-    for r in range(d):
-        terms = [(c, J[r, c]) for c in range(d) if J[r, c] != 0.0]
-        nnz += len(terms)
-        assert terms, "J has an empty row?"
-        # start with a +-1 coefficient if there is one (saves the multiply)
+    n = 2 * l + 1
+    NP, NS = len(d.pairs), len(d.singles)
+    o = []
+    o.append("template <> struct PDeg<%d> {" % l)
+    o.append("    static constexpr int NP = %d, NS = %d;" % (NP, NS))
+    o.append("    struct Vec { f32x2_t lo[%d], hi[%d]; float slo[%d], shi[%d]; float ctr; };" % (max(NP, 1), max(NP, 1), max(NS, 1), max(NS, 1)))
+    # ---- load / store (column with element stride st)
+    o.append("    template <bool G> static __device__ __forceinline__ void load(Vec& v, const float* __restrict__ s, int st) {")
+    for q, (m1, m2) in enumerate(d.pairs):
+        o.append("        v.lo[%d] = pk(ldf<G>(s + %d * st), ldf<G>(s + %d * st));" % (q, l - m1, l - m2))
+        o.append("        v.hi[%d] = pk(ldf<G>(s + %d * st), ldf<G>(s + %d * st));" % (q, l + m1, l + m2))
+    for s, m in enumerate(d.singles):
+        o.append("        v.slo[%d] = ldf<G>(s + %d * st); v.shi[%d] = ldf<G>(s + %d * st);" % (s, l - m, s, l + m))
+    o.append("        v.ctr = ldf<G>(s + %d * st);" % l)
+    o.append("    }")
+    o.append("    static __device__ __forceinline__ void store(const Vec& v, float* __restrict__ s, int st) {")
+    for i in range(n):
+        o.append("        s[%d * st] = %s;" % (i, d.acc(i, "v")))
+    o.append("    }")
+    # ---- pair rotations.  t = trig table of one angle: 4 x float4 (c_m1, c_m2, s_m1, s_m2)
+    o.append("    template <bool TR> static __device__ __forceinline__ void xrot(Vec& v, const float4* __restrict__ t) {")
+    slots = sorted(set([trig_pos(m1)[0] for m1, _ in d.pairs] + [trig_pos(m)[0] for m in d.singles]))
+    for sl in slots:
+        o.append("        const float4 t%d = t[%d];" % (sl, sl))
+    for q, (m1, m2) in enumerate(d.pairs):
+        sl, lane = trig_pos(m1)
+        assert lane == 0 and trig_pos(m2) == (sl, 1)
+        o.append("        { const f32x2_t C = pk(t%d.x, t%d.y), S = pk(t%d.z, t%d.w), P = v.lo[%d], Q = v.hi[%d];" % (sl, sl, sl, sl, q, q))
+        o.append("          const f32x2_t sq = mul2(S, Q), sp = mul2(S, P);")
+        o.append("          v.lo[%d] = fma2(C, P, TR ? neg2(sq) : sq); v.hi[%d] = fma2(C, Q, TR ? sp : neg2(sp)); }" % (q, q))
+    for s, m in enumerate(d.singles):
+        sl, lane = trig_pos(m)
+        c = "t%d.%s" % (sl, "xy"[lane])
+        sn = "t%d.%s" % (sl, "zw"[lane])
+        o.append("        { const float c = %s, s = TR ? -%s : %s, a = v.slo[%d], b = v.shi[%d];" % (c, sn, sn, s, s))
+        o.append("          v.slo[%d] = fmaf(c, a, s * b); v.shi[%d] = fmaf(c, b, -(s * a)); }" % (s, s))
+    if not slots:
+        o.append("        (void)v; (void)t;")
+    o.append("    }")
+    # ---- y = J x
+    o.append("    static __device__ __forceinline__ void jmul(const Vec& x, Vec& y) {")
+    n_f2 = n_f1 = 0
+
+    def scalar_row(r):
+        nonlocal n_f1
+        terms = [(c, J[r, c]) for c in range(n) if J[r, c] != 0.0]
+        assert terms
         terms.sort(key=lambda t: 0 if abs(abs(t[1]) - 1.0) < 1e-15 else 1)
         c0, v0 = terms[0]
         if abs(v0 - 1.0) < 1e-15:
-            expr = "x[%d]" % c0
+            e = d.acc(c0, "x")
         elif abs(v0 + 1.0) < 1e-15:
-            expr = "vneg(x[%d])" % c0
+            e = "-" + d.acc(c0, "x")
         else:
-            expr = "vmul(%s, x[%d])" % (lit(v0), c0)
+            e = "%s * %s" % (lit(v0), d.acc(c0, "x"))
+        n_f1 += len(terms)
         for c, v in terms[1:]:
-            expr = "vfma(%s, x[%d], %s)" % (lit(v), c, expr)
-        lines.append("    y[%d] = %s;" % (r, expr))
-    lines.append("}")
-    lines.append("};")
-    return "\n".join(lines), nnz
+            e = "fmaf(%s, %s, %s)" % (lit(v), d.acc(c, "x"), e)
+        return e
+
+    def pair_rows(r1, r2):
+        nonlocal n_f2
+        cols = [c for c in range(n) if J[r1, c] != 0.0 or J[r2, c] != 0.0]
+        s1 = sum(1 for c in cols if J[r1, c] != 0.0)
+        s2 = sum(1 for c in cols if J[r2, c] != 0.0)
+        assert len(cols) <= max(s1, s2) + 1, "rows %d,%d of J_%d do not share their support" % (r1, r2, l)
+        e = None
+        for c in cols:
+            k = len(ktab)
+            ktab.append((J[r1, c], J[r2, c]))
+            xb = "bc(%s)" % d.acc(c, "x")
+            e = "mul2(kj(%d), %s)" % (k, xb) if e is None else "fma2(kj(%d), %s, %s)" % (k, xb, e)
+            n_f2 += 1
+        return e
+
+    for q, (m1, m2) in enumerate(d.pairs):
+        o.append("        y.lo[%d] = %s;" % (q, pair_rows(l - m1, l - m2)))
+        o.append("        y.hi[%d] = %s;" % (q, pair_rows(l + m1, l + m2)))
+    for s, m in enumerate(d.singles):
+        o.append("        y.slo[%d] = %s;" % (s, scalar_row(l - m)))
+        o.append("        y.shi[%d] = %s;" % (s, scalar_row(l + m)))
+    o.append("        y.ctr = %s;" % scalar_row(l))
+    o.append("    }")
+    # ---- <h, G w> = sum_m m (h[l-m] w[l+m] - h[l+m] w[l-m]), accumulated into (ap: per-lane pair, as: scalar)
+    o.append("    static __device__ __forceinline__ void gdot(const Vec& h, const Vec& w, f32x2_t& ap, float& as) {")
+    for q, (m1, m2) in enumerate(d.pairs):
+        o.append("        ap = fma2(pk(%s, %s), fma2(neg2(h.hi[%d]), w.lo[%d], mul2(h.lo[%d], w.hi[%d])), ap);" % (lit(m1), lit(m2), q, q, q, q))
+    for s, m in enumerate(d.singles):
+        o.append("        as = fmaf(%s, fmaf(h.slo[%d], w.shi[%d], -(h.shi[%d] * w.slo[%d])), as);" % (lit(m), s, s, s, s))
+    if not d.pairs and not d.singles:
+        o.append("        (void)h; (void)w; (void)ap; (void)as;")
+    elif not d.pairs:
+        o.append("        (void)ap;")
+    elif not d.singles:
+        o.append("        (void)as;")
+    o.append("    }")
+    o.append("};")
+    return "\n".join(o), n_f2, n_f1
+
+
+HEADER = '''// GENERATED by tools/gen_wigner.py %(lmax)d -- do not edit by hand.
+// Per-degree operators of the Wigner chain  X(a) J X(b) J X(c)  on ONE column, in packed f32x2 form
+// (SASS FFMA2 / FMUL2: two FMAs per issue slot).  See the generator's docstring for the layout:
+// lo_m = x[l-m], hi_m = x[l+m]; frequencies of equal parity are paired (1,3) (5,7) | (2,4) (6,8);
+// unpaired frequencies and the centre stay scalar.  J_l coefficients of paired rows sit in constant memory
+// (kJ2, read through uniform registers); coefficients of scalar rows are immediates.
+#pragma once
+namespace lv { namespace wg2 {
+constexpr int kGenLmax = %(lmax)d;
+typedef unsigned long long f32x2_t;   // two floats in an aligned 64-bit register pair
+__device__ __forceinline__ f32x2_t pk(float a, float b) { f32x2_t r; asm("mov.b64 %%0, {%%1, %%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float plo(f32x2_t v) { float a, b; asm("mov.b64 {%%0, %%1}, %%2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
+__device__ __forceinline__ float phi(f32x2_t v) { float a, b; asm("mov.b64 {%%0, %%1}, %%2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+__device__ __forceinline__ f32x2_t bc(float a) { return pk(a, a); }                       // -> scalar-broadcast operand (R.F32)
+__device__ __forceinline__ f32x2_t neg2(f32x2_t v) { return pk(-plo(v), -phi(v)); }      // folds into an operand modifier
+__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) { f32x2_t r; asm("mul.rn.f32x2 %%0, %%1, %%2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) { f32x2_t r; asm("fma.rn.f32x2 %%0, %%1, %%2, %%3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+template <bool G> __device__ __forceinline__ float ldf(const float* p) { return G ? __ldg(p) : *p; }
+'''
 
 
 def main():
     lmax = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-    out = ["// GENERATED by tools/gen_wigner.py %d -- do not edit by hand." % lmax,
-           "// y = J_l x with J_l the Pinchon-Hoggan matrix of degree l (symmetric, involutive);",
-           "// one FMA per structural non-zero, coefficients as immediates.",
-           "#pragma once",
-           "namespace lv { namespace wg {",
-           "constexpr int kGenLmax = %d;" % lmax,
-           "// Element type V: float, or a packed pair of floats (two channels, Blackwell f32x2 arithmetic);",
-           "// vmul(k, x) = k*x, vfma(k, x, a) = k*x + a, vneg(x) = -x with k a scalar compile-time coefficient.",
-           "typedef unsigned long long f32x2_t;   // two floats in one 64-bit register pair (lo = first channel)",
-           "__device__ __forceinline__ float vmul(float k, float x) { return k * x; }",
-           "__device__ __forceinline__ float vfma(float k, float x, float a) { return fmaf(k, x, a); }",
-           "__device__ __forceinline__ float vneg(float x) { return -x; }",
-           "__device__ __forceinline__ f32x2_t vbc(float k) { f32x2_t r; asm(\"mov.b64 %0, {%1, %1};\" : \"=l\"(r) : \"f\"(k)); return r; }",
-           "__device__ __forceinline__ f32x2_t vmul(float k, f32x2_t x) { f32x2_t r; asm(\"mul.rn.f32x2 %0, %1, %2;\" : \"=l\"(r) : \"l\"(vbc(k)), \"l\"(x)); return r; }",
-           "__device__ __forceinline__ f32x2_t vfma(float k, f32x2_t x, f32x2_t a) { f32x2_t r; asm(\"fma.rn.f32x2 %0, %1, %2, %3;\" : \"=l\"(r) : \"l\"(vbc(k)), \"l\"(x), \"l\"(a)); return r; }",
-           "__device__ __forceinline__ f32x2_t vneg(f32x2_t x) { return vmul(-1.0f, x); }",
-           "template <int L> struct JMul;"]
-    counts = []
+    ktab = []
+    bodies, stats = [], []
     for l in range(lmax + 1):
-        code, nnz = emit_jmul(l)
-        counts.append(nnz)
-        out.append(code)
-    out.append("template <int L, typename V> __device__ __forceinline__ void jmul(const V (&x)[2 * L + 1], V (&y)[2 * L + 1]) { JMul<L>::mul(x, y); }")
-    out.append("// non-zeros per degree: %s (total %d)" % (counts, sum(counts)))
-    out.append("}}  // namespace lv::wg")
+        code, f2, f1 = emit(l, ktab)
+        bodies.append(code)
+        stats.append((f2, f1))
+    out = [HEADER % {"lmax": lmax}]
+    out.append("// (J[r1,c], J[r2,c]) for the paired rows, in order of use")
+    out.append("__constant__ __align__(16) float2 kJ2[%d] = {" % max(len(ktab), 1))
+    for i in range(0, len(ktab), 4):
+        out.append("    " + " ".join("{%s, %s}," % (lit(a), lit(b)) for a, b in ktab[i:i + 4]))
+    out.append("};")
+    out.append("__device__ __forceinline__ f32x2_t kj(int i) { return pk(kJ2[i].x, kJ2[i].y); }")
+    out.append("template <int L> struct PDeg;")
+    out.extend(bodies)
+    out.append("// J multiply, (packed FMAs, scalar FMAs) per degree: %s; issue slots %d (scalar form: 247)"
+               % (stats, sum(a + b for a, b in stats)))
+    out.append("}}  // namespace lv::wg2")
     path = os.path.join(ROOT, "lie_vae_b200", "csrc", "wigner_gen.cuh")
     with open(path, "w") as f:
         f.write("\n".join(out) + "\n")
-    print("wrote", path, "nnz", counts, sum(counts))
+    print("wrote", path, stats, "constants", len(ktab))
 
 
 if __name__ == "__main__":
