@@ -135,6 +135,40 @@ int lv_wigner_apply_bwd_f32(const float* angles, const float* spectrum, const fl
                             float* gspectrum, float* workspace, int64_t workspace_floats, int64_t N, int lmin,
                             int lmax, int C, int shared_spectrum, int transpose, void* stream);
 
+/* ---- the same action for ANY degree range (lmax <= lv_wigner_generic_max_degree()) and for float64: run-time loops over
+ *   a caller-owned dense J table `jtable` = J_0 | J_1 | ... | J_lmax (row-major (2l+1)^2 blocks, block l at offset
+ *   l(2l-1)(2l+1)/3; lie_tools.j_matrix lie_tools.py:10-14).  Covers what the unrolled kernels above do not
+ *   (degrees > 8, FP64).  Backward writes PER-COLUMN results: gangle_parts (N,C,3) -- sum over C for g_angles -- and
+ *   gspectrum (N,M,C) -- sum over N for a shared spectrum; the caller reduces (deterministic, no atomics). ---- */
+int lv_wigner_generic_max_degree(void);
+int lv_wigner_generic_fwd_f32(const float* angles, const float* spectrum, const float* jtable, float* out, int64_t N,
+                              int lmin, int lmax, int C, int shared_spectrum, int transpose, void* stream);
+int lv_wigner_generic_bwd_f32(const float* angles, const float* spectrum, const float* jtable, const float* gout,
+                              float* gangle_parts, float* gspectrum, int64_t N, int lmin, int lmax, int C,
+                              int shared_spectrum, int transpose, void* stream);
+int lv_wigner_generic_fwd_f64(const double* angles, const double* spectrum, const double* jtable, double* out, int64_t N,
+                              int lmin, int lmax, int C, int shared_spectrum, int transpose, void* stream);
+int lv_wigner_generic_bwd_f64(const double* angles, const double* spectrum, const double* jtable, const double* gout,
+                              double* gangle_parts, double* gspectrum, int64_t N, int lmin, int lmax, int C,
+                              int shared_spectrum, int transpose, void* stream);
+
+/* ---- the same action for ANY degree range (lmax <= lv_wigner_generic_max_degree()) and for float64: run-time loops over
+ *   a caller-owned dense J table `jtable` = J_0 | J_1 | ... | J_lmax (row-major (2l+1)^2 blocks, block l at offset
+ *   l(2l-1)(2l+1)/3; lie_tools.j_matrix lie_tools.py:10-14).  Covers what the unrolled kernels above do not
+ *   (degrees > 8, FP64).  Backward writes PER-COLUMN results: gangle_parts (N,C,3) -- sum over C for g_angles -- and
+ *   gspectrum (N,M,C) -- sum over N for a shared spectrum; the caller reduces (deterministic, no atomics). ---- */
+int lv_wigner_generic_max_degree(void);
+int lv_wigner_generic_fwd_f32(const float* angles, const float* spectrum, const float* jtable, float* out, int64_t N,
+                              int lmin, int lmax, int C, int shared_spectrum, int transpose, void* stream);
+int lv_wigner_generic_bwd_f32(const float* angles, const float* spectrum, const float* jtable, const float* gout,
+                              float* gangle_parts, float* gspectrum, int64_t N, int lmin, int lmax, int C,
+                              int shared_spectrum, int transpose, void* stream);
+int lv_wigner_generic_fwd_f64(const double* angles, const double* spectrum, const double* jtable, double* out, int64_t N,
+                              int lmin, int lmax, int C, int shared_spectrum, int transpose, void* stream);
+int lv_wigner_generic_bwd_f64(const double* angles, const double* spectrum, const double* jtable, const double* gout,
+                              double* gangle_parts, double* gspectrum, int64_t N, int lmin, int lmax, int C,
+                              int shared_spectrum, int transpose, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

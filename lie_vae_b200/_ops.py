@@ -263,3 +263,80 @@ class WignerApply(Function):
             _cabi.call("lv_wigner_apply_bwd_f32", _cabi.ptr(a_c), _cabi.ptr(s_c), _cabi.ptr(g), _cabi.ptr(gang),
                        _cabi.ptr(gspec), _cabi.ptr(ws), nws, N, lmin, lmax, C, int(shared), int(transpose), _stream())
         return gang, gspec, None, None, None
+
+
+# ------------------------------------------------------------------------------ generic Wigner action (any degree, f32 / f64)
+_J_TABLES = {}
+
+
+def _j_table(lmax, dtype, device):
+    """Packed dense J_0 | ... | J_lmax on `device` (cached; the C ABI takes it as a caller-owned pointer)."""
+    key = (int(lmax), dtype, str(device))
+    t = _J_TABLES.get(key)
+    if t is None:
+        import numpy as np
+        from .jmatrix import j_table
+        t = torch.from_numpy(j_table(int(lmax), np.float64)).to(device=device, dtype=dtype)
+        _J_TABLES[key] = t
+    return t
+
+
+def generic_max_degree():
+    return int(_cabi.lib().lv_wigner_generic_max_degree())
+
+
+class WignerApplyGeneric(Function):
+    """Same contract as WignerApply for any degree range up to generic_max_degree() and float32 / float64."""
+
+    @staticmethod
+    def forward(ctx, angles, spectrum, lmin, lmax, transpose):
+        dev = _require_cuda(angles, spectrum)
+        if angles.dtype != spectrum.dtype:
+            raise TypeError("angles and spectrum must share a dtype, got %s / %s" % (angles.dtype, spectrum.dtype))
+        sfx = _sfx(angles)
+        if angles.dim() != 2 or angles.shape[1] != 3:
+            raise ValueError("angles must be (N,3)")
+        if lmax > generic_max_degree():
+            raise NotImplementedError("degree %d > %d is not supported" % (lmax, generic_max_degree()))
+        N = angles.shape[0]
+        M = (lmax + 1) ** 2 - lmin ** 2
+        shared = spectrum.dim() == 2
+        if shared:
+            if spectrum.shape[0] != M:
+                raise ValueError("spectrum must have %d rows for degrees %d..%d, got %s" % (M, lmin, lmax, tuple(spectrum.shape)))
+        elif spectrum.dim() != 3 or spectrum.shape[0] != N or spectrum.shape[1] != M:
+            raise ValueError("spectrum must be (N=%d, M=%d, C), got %s" % (N, M, tuple(spectrum.shape)))
+        C = spectrum.shape[-1]
+        a_c, s_c = angles.contiguous(), spectrum.contiguous()
+        jt = _j_table(lmax, angles.dtype, dev)
+        out = torch.empty((N, M, C), dtype=angles.dtype, device=dev)
+        with torch.cuda.device(dev):
+            _cabi.call("lv_wigner_generic_fwd_" + sfx, _cabi.ptr(a_c), _cabi.ptr(s_c), _cabi.ptr(jt), _cabi.ptr(out), N, lmin, lmax,
+                       C, int(shared), int(bool(transpose)), _stream())
+        ctx.save_for_backward(a_c, s_c, jt)
+        ctx.meta = (N, M, lmin, lmax, C, shared, bool(transpose), sfx)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        a_c, s_c, jt = ctx.saved_tensors
+        N, M, lmin, lmax, C, shared, transpose, sfx = ctx.meta
+        dev = a_c.device
+        g = gout.contiguous()
+        parts = torch.empty((N, C, 3), dtype=a_c.dtype, device=dev)
+        gspec = torch.empty((N, M, C), dtype=a_c.dtype, device=dev)
+        with torch.cuda.device(dev):
+            _cabi.call("lv_wigner_generic_bwd_" + sfx, _cabi.ptr(a_c), _cabi.ptr(s_c), _cabi.ptr(jt), _cabi.ptr(g), _cabi.ptr(parts),
+                       _cabi.ptr(gspec), N, lmin, lmax, C, int(shared), int(transpose), _stream())
+        return parts.sum(1), (gspec.sum(0) if shared else gspec), None, None, None
+
+
+FAST_MAX_DEGREE = 8   # degrees covered by the unrolled, packed float32 kernels
+
+
+def wigner_apply(angles, spectrum, lmin, lmax, transpose=False):
+    """Dispatch: unrolled packed kernels for float32 and degrees <= 8, the generic kernels otherwise."""
+    if angles.dtype == torch.float32 and spectrum.dtype == torch.float32 and lmax <= FAST_MAX_DEGREE:
+        return WignerApply.apply(angles, spectrum, lmin, lmax, transpose)
+    return WignerApplyGeneric.apply(angles, spectrum, lmin, lmax, transpose)

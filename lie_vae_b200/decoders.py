@@ -54,7 +54,7 @@ class ActionNet(nn.Module):
         """Input is ZYZ Euler angles."""
         n, d = angles.shape
         assert d == 3, 'Input should be Euler angles.'
-        item = _ops.WignerApply.apply(angles, self.item_rep, 0, self.degrees, self.transpose) \
+        item = _ops.wigner_apply(angles, self.item_rep, 0, self.degrees, self.transpose) \
             .view(-1, self.matrix_dims * self.rep_copies)
         if self.mlp:
             item = self.mlp(item)

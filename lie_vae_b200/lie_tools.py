@@ -18,7 +18,7 @@ __all__ = ["j_matrix", "map_to_lie_algebra", "map_to_lie_vector", "rodrigues", "
            "quaternions_to_eazyz", "group_matrix_to_eazyz", "quaternions_to_group_matrix",
            "wigner_d_matrix", "block_wigner_matrix_multiply", "random_quaternions", "random_group_matrices"]
 
-MAX_DEGREE = 8   # degrees handled by the unrolled Wigner kernels
+MAX_DEGREE = 32   # degrees handled by the Wigner kernels (<= 8: unrolled packed float32 kernels; above, or float64: generic kernels)
 
 
 @lru_cache(maxsize=256)
@@ -111,7 +111,7 @@ def wigner_d_matrix(angles, degree):
     _check_degree(degree)
     d = 2 * degree + 1
     eye = torch.eye(d, dtype=angles.dtype, device=angles.device)
-    out = _ops.WignerApply.apply(angles.reshape(-1, 3), eye, degree, degree, False)
+    out = _ops.wigner_apply(angles.reshape(-1, 3), eye, degree, degree, False)
     return out.view(*batch_dims, d, d)
 
 
@@ -125,7 +125,7 @@ def block_wigner_matrix_multiply(angles, spectrum, max_degree, transpose=False):
     _check_degree(max_degree)
     if spectrum.dim() == 3 and spectrum.shape[0] != 1 and spectrum.stride(0) == 0:
         spectrum = spectrum[0]
-    return _ops.WignerApply.apply(angles, spectrum, 0, max_degree, transpose)
+    return _ops.wigner_apply(angles, spectrum, 0, max_degree, transpose)
 
 
 def random_quaternions(n, dtype=torch.float32, device=None):

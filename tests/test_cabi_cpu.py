@@ -93,5 +93,5 @@ def test_module_surface_matches_reference():
     buf = dc.ActionNet(2, torch.nn.Sequential(), item_rep=torch.zeros(9, 10))
     assert "item_rep" in dict(buf.named_buffers()) and not list(buf.parameters())
     with pytest.raises(NotImplementedError):
-        dc.ActionNet(9, torch.nn.Sequential())
+        dc.ActionNet(33, torch.nn.Sequential())
     assert tuple(lt.j_matrix(3).shape) == (7, 7) and lt.j_matrix(3).dtype == torch.float32

@@ -240,4 +240,4 @@ def test_errors(lt):
     with pytest.raises(AssertionError):
         lt.wigner_d_matrix(torch.randn(4, 2, device="cuda"), 1)
     with pytest.raises(NotImplementedError):
-        lt.wigner_d_matrix(torch.randn(4, 3, device="cuda"), 9)
+        lt.wigner_d_matrix(torch.randn(4, 3, device="cuda"), 33)

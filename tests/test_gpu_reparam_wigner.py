@@ -285,7 +285,7 @@ def test_wigner_errors(mods):
     lt, _, dc = mods
     a = torch.randn(4, 3, device="cuda")
     with pytest.raises(NotImplementedError):
-        lt.block_wigner_matrix_multiply(a, torch.randn(4, 100, 2, device="cuda"), 9)
+        lt.block_wigner_matrix_multiply(a, torch.randn(4, 34 * 34, 2, device="cuda"), 33)
     with pytest.raises(ValueError):
         lt.block_wigner_matrix_multiply(a, torch.randn(4, 10, 2, device="cuda"), 2)
     with pytest.raises(AssertionError):

@@ -84,7 +84,13 @@ def test_wigner_d():
         np.testing.assert_allclose(O.wigner_d_matrix(T(g["angles"]), l).numpy(), g["D%d" % l], **TOL)
 
 
-@pytest.mark.parametrize("tag", ["L8C3", "L3C1", "L5C10"])
+def test_wigner_d_high_degree():
+    g = load_golden("wigner_d_high")
+    for l in (9, 12, 16):
+        np.testing.assert_allclose(O.wigner_d_matrix(T(g["angles"]), l).numpy(), g["D%d" % l], rtol=1e-10, atol=1e-11)
+
+
+@pytest.mark.parametrize("tag", ["L8C3", "L3C1", "L5C10", "L11C2"])
 @pytest.mark.parametrize("tr", ["N", "T"])
 def test_block_wigner(tag, tr):
     g = load_golden("block_wigner_%s_%s" % (tag, tr))
@@ -94,7 +100,7 @@ def test_block_wigner(tag, tr):
                 dict(rtol=1e-10, atol=1e-11))
 
 
-@pytest.mark.parametrize("name", ["action_net_L8C10", "action_net_L3C3"])
+@pytest.mark.parametrize("name", ["action_net_L8C10", "action_net_L3C3", "action_net_L10C4"])
 def test_action_net(name):
     g = load_golden(name)
     L, tr = int(g["degrees"]), bool(int(g["transpose"]))
