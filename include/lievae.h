@@ -118,6 +118,17 @@ int lv_so3_reparam_eazyz_bwd_f32(const float* mu, const float* sigma, const floa
                                  const float* gangles, const float* glq, float* gmu, float* gsigma, int64_t n, int64_t B,
                                  int k, void* stream);
 
+/* float64 instantiations of the four entry points above (same contract; the winding terms use the library log/exp) */
+int lv_so3_reparam_fwd_f64(const double* mu, const double* sigma, const double* eps, double* z, double* log_q,
+                           int64_t n, int64_t B, int k, void* stream);
+int lv_so3_reparam_bwd_f64(const double* mu, const double* sigma, const double* eps, const double* gz, const double* glq,
+                           double* gmu, double* gsigma, int64_t n, int64_t B, int k, void* stream);
+int lv_so3_reparam_eazyz_fwd_f64(const double* mu, const double* sigma, const double* eps, double* z, double* angles,
+                                 double* log_q, int64_t n, int64_t B, int k, void* stream);
+int lv_so3_reparam_eazyz_bwd_f64(const double* mu, const double* sigma, const double* eps, const double* gz,
+                                 const double* gangles, const double* glq, double* gmu, double* gsigma, int64_t n, int64_t B,
+                                 int k, void* stream);
+
 /* ---- block-diagonal Wigner-D action on a spectrum, degrees lmin..lmax (<= 8), C channels.
  *   block_wigner_matrix_multiply lie_tools.py:226-253, wigner_d_matrix lie_tools.py:211-223,
  *   _z_rot_mat lie_tools.py:195-208, ActionNet.forward decoders.py:47-56.

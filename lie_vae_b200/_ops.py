@@ -126,14 +126,15 @@ def sum_leading(t):
 
 # ------------------------------------------------------------------------------ fused SO(3) reparameterize
 class SO3Reparam(Function):
-    """(mu (B,3,3), sigma (B,3), eps (n,B,3), k) -> z (n,B,3,3), log_q (n,B).   float32."""
+    """(mu (B,3,3), sigma (B,3), eps (n,B,3), k) -> z (n,B,3,3), log_q (n,B).   float32 (production) or float64."""
 
     @staticmethod
     def forward(ctx, mu, sigma, eps, k):
         dev = _require_cuda(mu, sigma, eps)
-        for t in (mu, sigma, eps):
-            if t.dtype != torch.float32:
-                raise TypeError("so3_reparameterize is float32 only, got %s" % t.dtype)
+        sfx = _sfx(mu)
+        for t in (sigma, eps):
+            if t.dtype != mu.dtype:
+                raise TypeError("so3_reparameterize: mu, sigma, eps must share a dtype, got %s / %s" % (mu.dtype, t.dtype))
         if mu.dim() != 3 or tuple(mu.shape[1:]) != (3, 3):
             raise ValueError("mu must be (B,3,3), got %s" % (tuple(mu.shape),))
         B = mu.shape[0]
@@ -143,10 +144,10 @@ class SO3Reparam(Function):
             raise ValueError("eps must be (n,B,3), got %s" % (tuple(eps.shape),))
         n = eps.shape[0]
         mu_c, sg_c, ep_c = mu.contiguous(), sigma.contiguous(), eps.contiguous()
-        z = torch.empty((n, B, 3, 3), dtype=torch.float32, device=dev)
-        log_q = torch.empty((n, B), dtype=torch.float32, device=dev)
+        z = torch.empty((n, B, 3, 3), dtype=mu.dtype, device=dev)
+        log_q = torch.empty((n, B), dtype=mu.dtype, device=dev)
         with torch.cuda.device(dev):
-            _cabi.call("lv_so3_reparam_fwd_f32", _cabi.ptr(mu_c), _cabi.ptr(sg_c), _cabi.ptr(ep_c), _cabi.ptr(z),
+            _cabi.call("lv_so3_reparam_fwd_" + sfx, _cabi.ptr(mu_c), _cabi.ptr(sg_c), _cabi.ptr(ep_c), _cabi.ptr(z),
                        _cabi.ptr(log_q), n, B, int(k), _stream())
         ctx.save_for_backward(mu_c, sg_c, ep_c)
         ctx.k = int(k)
@@ -160,10 +161,10 @@ class SO3Reparam(Function):
         dev = mu.device
         gz = None if gz is None else gz.contiguous()
         glq = None if glq is None else glq.contiguous()
-        gmu = torch.empty((n, B, 3, 3), dtype=torch.float32, device=dev)
-        gsg = torch.empty((n, B, 3), dtype=torch.float32, device=dev)
+        gmu = torch.empty((n, B, 3, 3), dtype=mu.dtype, device=dev)
+        gsg = torch.empty((n, B, 3), dtype=mu.dtype, device=dev)
         with torch.cuda.device(dev):
-            _cabi.call("lv_so3_reparam_bwd_f32", _cabi.ptr(mu), _cabi.ptr(sigma), _cabi.ptr(eps), _cabi.ptr(gz),
+            _cabi.call("lv_so3_reparam_bwd_" + _sfx(mu), _cabi.ptr(mu), _cabi.ptr(sigma), _cabi.ptr(eps), _cabi.ptr(gz),
                        _cabi.ptr(glq), _cabi.ptr(gmu), _cabi.ptr(gsg), n, B, ctx.k, _stream())
         return sum_leading(gmu), sum_leading(gsg), None, None
 
@@ -178,9 +179,10 @@ class SO3ReparamEazyz(Function):
     @staticmethod
     def forward(ctx, mu, sigma, eps, k):
         dev = _require_cuda(mu, sigma, eps)
-        for t in (mu, sigma, eps):
-            if t.dtype != torch.float32:
-                raise TypeError("so3_reparameterize_eazyz is float32 only, got %s" % t.dtype)
+        sfx = _sfx(mu)
+        for t in (sigma, eps):
+            if t.dtype != mu.dtype:
+                raise TypeError("so3_reparameterize_eazyz: mu, sigma, eps must share a dtype, got %s / %s" % (mu.dtype, t.dtype))
         if mu.dim() != 3 or tuple(mu.shape[1:]) != (3, 3):
             raise ValueError("mu must be (B,3,3), got %s" % (tuple(mu.shape),))
         B = mu.shape[0]
@@ -190,10 +192,10 @@ class SO3ReparamEazyz(Function):
             raise ValueError("eps must be (n,B,3), got %s" % (tuple(eps.shape),))
         n = eps.shape[0]
         mu_c, sg_c, ep_c = mu.contiguous(), sigma.contiguous(), eps.contiguous()
-        angles = torch.empty((n, B, 3), dtype=torch.float32, device=dev)
-        log_q = torch.empty((n, B), dtype=torch.float32, device=dev)
+        angles = torch.empty((n, B, 3), dtype=mu.dtype, device=dev)
+        log_q = torch.empty((n, B), dtype=mu.dtype, device=dev)
         with torch.cuda.device(dev):
-            _cabi.call("lv_so3_reparam_eazyz_fwd_f32", _cabi.ptr(mu_c), _cabi.ptr(sg_c), _cabi.ptr(ep_c), None,
+            _cabi.call("lv_so3_reparam_eazyz_fwd_" + sfx, _cabi.ptr(mu_c), _cabi.ptr(sg_c), _cabi.ptr(ep_c), None,
                        _cabi.ptr(angles), _cabi.ptr(log_q), n, B, int(k), _stream())
         ctx.save_for_backward(mu_c, sg_c, ep_c)
         ctx.k = int(k)
@@ -205,12 +207,12 @@ class SO3ReparamEazyz(Function):
         mu, sigma, eps = ctx.saved_tensors
         n, B = eps.shape[0], eps.shape[1]
         dev = mu.device
-        gang = torch.zeros((n, B, 3), dtype=torch.float32, device=dev) if gang is None else gang.contiguous()
+        gang = torch.zeros((n, B, 3), dtype=mu.dtype, device=dev) if gang is None else gang.contiguous()
         glq = None if glq is None else glq.contiguous()
-        gmu = torch.empty((n, B, 3, 3), dtype=torch.float32, device=dev)
-        gsg = torch.empty((n, B, 3), dtype=torch.float32, device=dev)
+        gmu = torch.empty((n, B, 3, 3), dtype=mu.dtype, device=dev)
+        gsg = torch.empty((n, B, 3), dtype=mu.dtype, device=dev)
         with torch.cuda.device(dev):
-            _cabi.call("lv_so3_reparam_eazyz_bwd_f32", _cabi.ptr(mu), _cabi.ptr(sigma), _cabi.ptr(eps), None, _cabi.ptr(gang),
+            _cabi.call("lv_so3_reparam_eazyz_bwd_" + _sfx(mu), _cabi.ptr(mu), _cabi.ptr(sigma), _cabi.ptr(eps), None, _cabi.ptr(gang),
                        _cabi.ptr(glq), _cabi.ptr(gmu), _cabi.ptr(gsg), n, B, ctx.k, _stream())
         return sum_leading(gmu), sum_leading(gsg), None, None
 

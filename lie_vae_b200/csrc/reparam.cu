@@ -1,4 +1,4 @@
-// Fused SO(3) reparameterize + wrapped log-density, forward and backward (sm_100a, FP32).
+// Fused SO(3) reparameterize + wrapped log-density, forward and backward (sm_100a; FP32 in production, FP64 instantiation).
 //
 // Replaces, with ONE kernel per direction, the ~760 ATen launches behind
 //   N0reparameterize.nsample            reparameterize.py:137-141   v = eps * sigma
@@ -24,93 +24,105 @@
 
 namespace lv {
 
-constexpr int RP_TILE = 256;
-constexpr float RP_CLAMP = 1e-3f;
-constexpr float RP_TWO_PI = 6.283185307179586f;
-constexpr float RP_LOG_2PI_1P5 = 2.756815599614018f;   // 1.5 * log(2 pi)
+constexpr int RP_TILE = 256;          // float; the double instantiation uses 128-sample tiles (same smem footprint)
+constexpr double RP_CLAMP = 1e-3;
+constexpr double RP_TWO_PI = 6.283185307179586476925;
+constexpr double RP_LOG_2PI_1P5 = 2.756815599614018102;   // 1.5 * log(2 pi)
+
+// per-term log / exp / divide: fast intrinsics in float (one MUFU each; the final log of the LSE is full precision),
+// the library functions in double
+__device__ __forceinline__ float rp_log(float x) { return __logf(x); }
+__device__ __forceinline__ float rp_exp(float x) { return __expf(x); }
+__device__ __forceinline__ float rp_div(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ double rp_log(double x) { return ::log(x); }
+__device__ __forceinline__ double rp_exp(double x) { return ::exp(x); }
+__device__ __forceinline__ double rp_div(double a, double b) { return a / b; }
+template <typename T> __device__ __forceinline__ T rp_neg_inf();
+template <> __device__ __forceinline__ float rp_neg_inf<float>() { return -INFINITY; }
+template <> __device__ __forceinline__ double rp_neg_inf<double>() { return -HUGE_VAL; }
 
 // ------------------------------------------------------------------ wrapped log-density terms
 // KT > 0: winding count known at compile time (terms live in registers, one pass of logs);
 // KT == 0: runtime K, two passes (max, then sum) recomputing the terms.
-template <int KT>
-__device__ __forceinline__ float winding_lse(float theta, float a, int krt) {
+template <typename T, int KT>
+__device__ __forceinline__ T winding_lse(T theta, T a, int krt) {
     if constexpr (KT > 0) {
-        float t[2 * KT + 1];
-        float m = -INFINITY;
+        T t[2 * KT + 1];
+        T m = rp_neg_inf<T>();
 #pragma unroll
         for (int i = 0; i < 2 * KT + 1; ++i) {
-            const float th = theta + RP_TWO_PI * float(i - KT);
-            const float x = th * th;
-            t[i] = fmaf(-a, x, __logf(fmaxf(x, RP_CLAMP)));
-            m = fmaxf(m, t[i]);
+            const T th = theta + T(RP_TWO_PI) * T(i - KT);
+            const T x = th * th;
+            t[i] = Sc<T>::fma(-a, x, rp_log(Sc<T>::max(x, T(RP_CLAMP))));
+            m = Sc<T>::max(m, t[i]);
         }
-        float s = 0.f;
+        T s = T(0);
 #pragma unroll
-        for (int i = 0; i < 2 * KT + 1; ++i) s += __expf(t[i] - m);
-        return m + logf(s);
+        for (int i = 0; i < 2 * KT + 1; ++i) s += rp_exp(t[i] - m);
+        return m + Sc<T>::log(s);
     } else {
-        float m = -INFINITY;
+        T m = rp_neg_inf<T>();
         for (int k = -krt; k <= krt; ++k) {
-            const float th = theta + RP_TWO_PI * float(k);
-            const float x = th * th;
-            m = fmaxf(m, fmaf(-a, x, __logf(fmaxf(x, RP_CLAMP))));
+            const T th = theta + T(RP_TWO_PI) * T(k);
+            const T x = th * th;
+            m = Sc<T>::max(m, Sc<T>::fma(-a, x, rp_log(Sc<T>::max(x, T(RP_CLAMP)))));
         }
-        float s = 0.f;
+        T s = T(0);
         for (int k = -krt; k <= krt; ++k) {
-            const float th = theta + RP_TWO_PI * float(k);
-            const float x = th * th;
-            s += __expf(fmaf(-a, x, __logf(fmaxf(x, RP_CLAMP))) - m);
+            const T th = theta + T(RP_TWO_PI) * T(k);
+            const T x = th * th;
+            s += rp_exp(Sc<T>::fma(-a, x, rp_log(Sc<T>::max(x, T(RP_CLAMP)))) - m);
         }
-        return m + logf(s);
+        return m + Sc<T>::log(s);
     }
 }
 
 // softmax-weighted sums needed by the backward:
 //   d1 = sum_k w_k (-2 a th_k + [th_k^2 >= c] 2/th_k)    (d LSE / d theta)
 //   e2 = sum_k w_k th_k^2                                 (-d LSE / d a)
-template <int KT>
-__device__ __forceinline__ void winding_grad(float theta, float a, int krt, float* d1, float* e2) {
-    float m = -INFINITY;
+template <typename T, int KT>
+__device__ __forceinline__ void winding_grad(T theta, T a, int krt, T* d1, T* e2) {
+    T m = rp_neg_inf<T>();
     if constexpr (KT > 0) {
-        float t[2 * KT + 1];
+        T t[2 * KT + 1];
 #pragma unroll
         for (int i = 0; i < 2 * KT + 1; ++i) {
-            const float th = theta + RP_TWO_PI * float(i - KT);
-            const float x = th * th;
-            t[i] = fmaf(-a, x, __logf(fmaxf(x, RP_CLAMP)));
-            m = fmaxf(m, t[i]);
+            const T th = theta + T(RP_TWO_PI) * T(i - KT);
+            const T x = th * th;
+            t[i] = Sc<T>::fma(-a, x, rp_log(Sc<T>::max(x, T(RP_CLAMP))));
+            m = Sc<T>::max(m, t[i]);
         }
-        float s = 0.f, s1 = 0.f, s2 = 0.f;
+        T s = T(0), s1 = T(0), s2 = T(0);
 #pragma unroll
         for (int i = 0; i < 2 * KT + 1; ++i) {
-            const float th = theta + RP_TWO_PI * float(i - KT);
-            const float x = th * th;
-            const float e = __expf(t[i] - m);
-            const float dl = x >= RP_CLAMP ? __fdividef(2.f, th) : 0.f;
+            const T th = theta + T(RP_TWO_PI) * T(i - KT);
+            const T x = th * th;
+            const T e = rp_exp(t[i] - m);
+            const T dl = x >= T(RP_CLAMP) ? rp_div(T(2), th) : T(0);
             s += e;
-            s1 = fmaf(e, fmaf(-2.f * a, th, dl), s1);
-            s2 = fmaf(e, x, s2);
+            s1 = Sc<T>::fma(e, Sc<T>::fma(T(-2) * a, th, dl), s1);
+            s2 = Sc<T>::fma(e, x, s2);
         }
-        const float inv = 1.f / s;
+        const T inv = T(1) / s;
         *d1 = s1 * inv;
         *e2 = s2 * inv;
     } else {
         for (int k = -krt; k <= krt; ++k) {
-            const float th = theta + RP_TWO_PI * float(k);
-            const float x = th * th;
-            m = fmaxf(m, fmaf(-a, x, __logf(fmaxf(x, RP_CLAMP))));
+            const T th = theta + T(RP_TWO_PI) * T(k);
+            const T x = th * th;
+            m = Sc<T>::max(m, Sc<T>::fma(-a, x, rp_log(Sc<T>::max(x, T(RP_CLAMP)))));
         }
-        float s = 0.f, s1 = 0.f, s2 = 0.f;
+        T s = T(0), s1 = T(0), s2 = T(0);
         for (int k = -krt; k <= krt; ++k) {
-            const float th = theta + RP_TWO_PI * float(k);
-            const float x = th * th;
-            const float e = __expf(fmaf(-a, x, __logf(fmaxf(x, RP_CLAMP))) - m);
-            const float dl = x >= RP_CLAMP ? __fdividef(2.f, th) : 0.f;
+            const T th = theta + T(RP_TWO_PI) * T(k);
+            const T x = th * th;
+            const T e = rp_exp(Sc<T>::fma(-a, x, rp_log(Sc<T>::max(x, T(RP_CLAMP)))) - m);
+            const T dl = x >= T(RP_CLAMP) ? rp_div(T(2), th) : T(0);
             s += e;
-            s1 = fmaf(e, fmaf(-2.f * a, th, dl), s1);
-            s2 = fmaf(e, x, s2);
+            s1 = Sc<T>::fma(e, Sc<T>::fma(T(-2) * a, th, dl), s1);
+            s2 = Sc<T>::fma(e, x, s2);
         }
-        const float inv = 1.f / s;
+        const T inv = T(1) / s;
         *d1 = s1 * inv;
         *e2 = s2 * inv;
     }
@@ -118,8 +130,8 @@ __device__ __forceinline__ void winding_grad(float theta, float a, int krt, floa
 
 // ------------------------------------------------------------------ staging of broadcast rows
 // rows [i0, i0+rows) of a (n,B,W) view of a (B,W) tensor: contiguous unless the tile wraps.
-template <int W>
-__device__ __forceinline__ void stage_bcast(float* __restrict__ dst, const float* __restrict__ src,
+template <typename T, int W>
+__device__ __forceinline__ void stage_bcast(T* __restrict__ dst, const T* __restrict__ src,
                                             int64_t i0, int rows, int64_t B) {
     // n == 1 (the training case): rows are not broadcast and the emulated 64-bit modulo is skipped
     const int64_t b0 = i0 < B ? i0 : i0 % B;
@@ -136,52 +148,52 @@ __device__ __forceinline__ void stage_bcast(float* __restrict__ dst, const float
 // ------------------------------------------------------------------ forward
 // EULER: additionally emit the ZYZ Euler angles of z (group_matrix_to_eazyz, lie_tools.py:178-180 -- what
 // VAE.decode feeds the action decoder, vae.py:182) from the registers that hold z; z itself is then optional.
-template <int KT, bool EULER>
-__global__ void __launch_bounds__(RP_TILE)
-so3_reparam_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ sigma, const float* __restrict__ eps,
-                       float* __restrict__ z, float* __restrict__ angles, float* __restrict__ log_q, int64_t total,
+template <typename T, int KT, bool EULER, int TILE>
+__global__ void __launch_bounds__(TILE)
+so3_reparam_fwd_kernel(const T* __restrict__ mu, const T* __restrict__ sigma, const T* __restrict__ eps,
+                       T* __restrict__ z, T* __restrict__ angles, T* __restrict__ log_q, int64_t total,
                        int64_t B, int krt) {
-    __shared__ __align__(16) float s_m[RP_TILE * 9];   // mu in, z out (same row, same thread)
-    __shared__ __align__(16) float s_s[RP_TILE * 3];
-    __shared__ __align__(16) float s_e[RP_TILE * 3];   // eps in, Euler angles out
-    const int64_t i0 = int64_t(blockIdx.x) * RP_TILE;
-    const int rows = int(min(int64_t(RP_TILE), total - i0));
-    stage_bcast<9>(s_m, mu, i0, rows, B);
-    stage_bcast<3>(s_s, sigma, i0, rows, B);
+    __shared__ __align__(16) T s_m[TILE * 9];   // mu in, z out (same row, same thread)
+    __shared__ __align__(16) T s_s[TILE * 3];
+    __shared__ __align__(16) T s_e[TILE * 3];   // eps in, Euler angles out
+    const int64_t i0 = int64_t(blockIdx.x) * TILE;
+    const int rows = int(min(int64_t(TILE), total - i0));
+    stage_bcast<T, 9>(s_m, mu, i0, rows, B);
+    stage_bcast<T, 3>(s_s, sigma, i0, rows, B);
     tile_g2s(s_e, eps + i0 * 3, rows * 3);
     tile_async_wait();
     __syncthreads();
     const int t = threadIdx.x;
     if (t < rows) {
-        float m[9], sg[3], v[3];
+        T m[9], sg[3], v[3];
 #pragma unroll
         for (int j = 0; j < 9; ++j) m[j] = s_m[t * 9 + j];
 #pragma unroll
         for (int j = 0; j < 3; ++j) { sg[j] = s_s[t * 3 + j]; v[j] = s_e[t * 3 + j] * sg[j]; }
-        RodriguesCtx<float> k;
+        RodriguesCtx<T> k;
         rodrigues_ctx(v, k);
-        float R[9], zr[9];
+        T R[9], zr[9];
         axis_angle_matrix(k.u, k.s, k.w, R);
 #pragma unroll
         for (int r = 0; r < 3; ++r)
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                zr[r * 3 + c] = fmaf(m[r * 3], R[c], fmaf(m[r * 3 + 1], R[3 + c], m[r * 3 + 2] * R[6 + c]));
+                zr[r * 3 + c] = Sc<T>::fma(m[r * 3], R[c], Sc<T>::fma(m[r * 3 + 1], R[3 + c], m[r * 3 + 2] * R[6 + c]));
                 s_m[t * 9 + r * 3 + c] = zr[r * 3 + c];
             }
         if (EULER) {
-            float q[4], e[3];
+            T q[4], e[3];
             mat_to_quat_fwd(zr, q);
             quat_to_eazyz_fwd(q, e);
 #pragma unroll
             for (int j = 0; j < 3; ++j) s_e[t * 3 + j] = e[j];
         }
         if (log_q != nullptr) {
-            const float q0 = k.u[0] / sg[0], q1 = k.u[1] / sg[1], q2 = k.u[2] / sg[2];
-            const float a = 0.5f * (q0 * q0 + q1 * q1 + q2 * q2);
-            const float lse = winding_lse<KT>(k.theta, a, krt);
-            const float den = fmaxf(2.f * k.w, RP_CLAMP);
-            log_q[i0 + t] = lse - (logf(sg[0]) + logf(sg[1]) + logf(sg[2])) - RP_LOG_2PI_1P5 - logf(den);
+            const T q0 = k.u[0] / sg[0], q1 = k.u[1] / sg[1], q2 = k.u[2] / sg[2];
+            const T a = T(0.5) * (q0 * q0 + q1 * q1 + q2 * q2);
+            const T lse = winding_lse<T, KT>(k.theta, a, krt);
+            const T den = Sc<T>::max(T(2) * k.w, T(RP_CLAMP));
+            log_q[i0 + t] = lse - (Sc<T>::log(sg[0]) + Sc<T>::log(sg[1]) + Sc<T>::log(sg[2])) - T(RP_LOG_2PI_1P5) - Sc<T>::log(den);
         }
     }
     __syncthreads();
@@ -193,20 +205,20 @@ so3_reparam_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ s
 // per-sample gradients: g_mu (total,9), g_sigma (total,3); for n > 1 the caller sums over n
 // (lv_sum_leading_f32).  EULER: the upstream gradient arrives (also) as g_angles and is pulled back
 // through matrix -> quaternion -> Euler on the recomputed z.
-template <int KT, bool EULER>
-__global__ void __launch_bounds__(RP_TILE)
-so3_reparam_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ sigma, const float* __restrict__ eps,
-                       const float* __restrict__ gz, const float* __restrict__ gangles, const float* __restrict__ glq,
-                       float* __restrict__ gmu, float* __restrict__ gsigma, int64_t total, int64_t B, int krt) {
-    __shared__ __align__(16) float s_m[RP_TILE * 9];
-    __shared__ __align__(16) float s_g[RP_TILE * 9];   // gz in, g_mu out
-    __shared__ __align__(16) float s_s[RP_TILE * 3];
-    __shared__ __align__(16) float s_e[RP_TILE * 3];   // eps in, g_sigma out
-    __shared__ __align__(16) float s_a[EULER ? RP_TILE * 3 : 4];   // g_angles in
-    const int64_t i0 = int64_t(blockIdx.x) * RP_TILE;
-    const int rows = int(min(int64_t(RP_TILE), total - i0));
-    stage_bcast<9>(s_m, mu, i0, rows, B);
-    stage_bcast<3>(s_s, sigma, i0, rows, B);
+template <typename T, int KT, bool EULER, int TILE>
+__global__ void __launch_bounds__(TILE)
+so3_reparam_bwd_kernel(const T* __restrict__ mu, const T* __restrict__ sigma, const T* __restrict__ eps,
+                       const T* __restrict__ gz, const T* __restrict__ gangles, const T* __restrict__ glq,
+                       T* __restrict__ gmu, T* __restrict__ gsigma, int64_t total, int64_t B, int krt) {
+    __shared__ __align__(16) T s_m[TILE * 9];
+    __shared__ __align__(16) T s_g[TILE * 9];   // gz in, g_mu out
+    __shared__ __align__(16) T s_s[TILE * 3];
+    __shared__ __align__(16) T s_e[TILE * 3];   // eps in, g_sigma out
+    __shared__ __align__(16) T s_a[EULER ? TILE * 3 : 4];   // g_angles in
+    const int64_t i0 = int64_t(blockIdx.x) * TILE;
+    const int rows = int(min(int64_t(TILE), total - i0));
+    stage_bcast<T, 9>(s_m, mu, i0, rows, B);
+    stage_bcast<T, 3>(s_s, sigma, i0, rows, B);
     tile_g2s(s_e, eps + i0 * 3, rows * 3);
     if (gz != nullptr) tile_g2s(s_g, gz + i0 * 9, rows * 9);
     if (EULER) tile_g2s(s_a, gangles + i0 * 3, rows * 3);
@@ -214,22 +226,22 @@ so3_reparam_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ s
     __syncthreads();
     const int t = threadIdx.x;
     if (t < rows) {
-        float m[9], G[9], sg[3], ep[3], v[3];
+        T m[9], G[9], sg[3], ep[3], v[3];
 #pragma unroll
-        for (int j = 0; j < 9; ++j) { m[j] = s_m[t * 9 + j]; G[j] = gz != nullptr ? s_g[t * 9 + j] : 0.f; }
+        for (int j = 0; j < 9; ++j) { m[j] = s_m[t * 9 + j]; G[j] = gz != nullptr ? s_g[t * 9 + j] : T(0); }
 #pragma unroll
         for (int j = 0; j < 3; ++j) { sg[j] = s_s[t * 3 + j]; ep[j] = s_e[t * 3 + j]; v[j] = ep[j] * sg[j]; }
-        RodriguesCtx<float> k;
+        RodriguesCtx<T> k;
         rodrigues_ctx(v, k);
-        float R[9];
+        T R[9];
         axis_angle_matrix(k.u, k.s, k.w, R);
         if (EULER) {
-            float zr[9], q[4], ge[3], gq[4], gze[9];
+            T zr[9], q[4], ge[3], gq[4], gze[9];
 #pragma unroll
             for (int r = 0; r < 3; ++r)
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
-                    zr[r * 3 + c] = fmaf(m[r * 3], R[c], fmaf(m[r * 3 + 1], R[3 + c], m[r * 3 + 2] * R[6 + c]));
+                    zr[r * 3 + c] = Sc<T>::fma(m[r * 3], R[c], Sc<T>::fma(m[r * 3 + 1], R[3 + c], m[r * 3 + 2] * R[6 + c]));
 #pragma unroll
             for (int j = 0; j < 3; ++j) ge[j] = s_a[t * 3 + j];
             mat_to_quat_fwd(zr, q);
@@ -239,39 +251,39 @@ so3_reparam_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ s
             for (int j = 0; j < 9; ++j) G[j] += gze[j];
         }
         // z = mu R:  g_mu = gz R^T,  g_R = mu^T gz
-        float gR[9];
+        T gR[9];
 #pragma unroll
         for (int r = 0; r < 3; ++r)
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                s_g[t * 9 + r * 3 + c] = fmaf(G[r * 3], R[c * 3], fmaf(G[r * 3 + 1], R[c * 3 + 1], G[r * 3 + 2] * R[c * 3 + 2]));
-                gR[r * 3 + c] = fmaf(m[r], G[c], fmaf(m[3 + r], G[3 + c], m[6 + r] * G[6 + c]));
+                s_g[t * 9 + r * 3 + c] = Sc<T>::fma(G[r * 3], R[c * 3], Sc<T>::fma(G[r * 3 + 1], R[c * 3 + 1], G[r * 3 + 2] * R[c * 3 + 2]));
+                gR[r * 3 + c] = Sc<T>::fma(m[r], G[c], Sc<T>::fma(m[3 + r], G[3 + c], m[6 + r] * G[6 + c]));
             }
-        float gth, gu[3];
+        T gth, gu[3];
         rodrigues_bwd_theta_u(k, gR, &gth, gu);
-        float gs_direct[3] = {0.f, 0.f, 0.f};
-        const float gl = glq != nullptr ? glq[i0 + t] : 0.f;
+        T gs_direct[3] = {T(0), T(0), T(0)};
+        const T gl = glq != nullptr ? glq[i0 + t] : T(0);
         if (glq != nullptr) {
-            const float is0 = 1.f / sg[0], is1 = 1.f / sg[1], is2 = 1.f / sg[2];
-            const float q0 = k.u[0] * is0, q1 = k.u[1] * is1, q2 = k.u[2] * is2;
-            const float a = 0.5f * (q0 * q0 + q1 * q1 + q2 * q2);
-            float d1, e2;
-            winding_grad<KT>(k.theta, a, krt, &d1, &e2);
+            const T is0 = T(1) / sg[0], is1 = T(1) / sg[1], is2 = T(1) / sg[2];
+            const T q0 = k.u[0] * is0, q1 = k.u[1] * is1, q2 = k.u[2] * is2;
+            const T a = T(0.5) * (q0 * q0 + q1 * q1 + q2 * q2);
+            T d1, e2;
+            winding_grad<T, KT>(k.theta, a, krt, &d1, &e2);
             // - d/dtheta log max(2w, c), 2w = 2 - 2cos: (2 sin)/(2w) = s/w where not clamped
-            const float dden = (2.f * k.w >= RP_CLAMP) ? k.s / k.w : 0.f;
-            gth = fmaf(gl, d1 - dden, gth);
+            const T dden = (T(2) * k.w >= T(RP_CLAMP)) ? k.s / k.w : T(0);
+            gth = Sc<T>::fma(gl, d1 - dden, gth);
             // d log_q / d a = -e2 ; d a / d u_i = u_i / sigma_i^2 ; d a / d sigma_i = -u_i^2 / sigma_i^3
-            gu[0] = fmaf(-gl * e2, q0 * is0, gu[0]);
-            gu[1] = fmaf(-gl * e2, q1 * is1, gu[1]);
-            gu[2] = fmaf(-gl * e2, q2 * is2, gu[2]);
-            gs_direct[0] = gl * (e2 * q0 * q0 - 1.f) * is0;
-            gs_direct[1] = gl * (e2 * q1 * q1 - 1.f) * is1;
-            gs_direct[2] = gl * (e2 * q2 * q2 - 1.f) * is2;
+            gu[0] = Sc<T>::fma(-gl * e2, q0 * is0, gu[0]);
+            gu[1] = Sc<T>::fma(-gl * e2, q1 * is1, gu[1]);
+            gu[2] = Sc<T>::fma(-gl * e2, q2 * is2, gu[2]);
+            gs_direct[0] = gl * (e2 * q0 * q0 - T(1)) * is0;
+            gs_direct[1] = gl * (e2 * q1 * q1 - T(1)) * is1;
+            gs_direct[2] = gl * (e2 * q2 * q2 - T(1)) * is2;
         }
-        float gv[3];
+        T gv[3];
         theta_u_to_v(k, gth, gu, gv);
 #pragma unroll
-        for (int j = 0; j < 3; ++j) s_e[t * 3 + j] = fmaf(gv[j], ep[j], gs_direct[j]);
+        for (int j = 0; j < 3; ++j) s_e[t * 3 + j] = Sc<T>::fma(gv[j], ep[j], gs_direct[j]);
     }
     __syncthreads();
     tile_s2g(gmu + i0 * 9, s_g, rows * 9);
@@ -284,29 +296,31 @@ so3_reparam_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ s
 static int reparam_check(const char* name, int64_t n, int64_t B, int k) {
     if (n < 0 || B < 0 || k < 0) { lv::set_error("%s: negative size", name); return LV_ERR_ARG; }
     if (k > 64) { lv::set_error("%s: k=%d winding terms unsupported (max 64)", name, k); return LV_ERR_UNSUPPORTED; }
-    if ((n * B + lv::RP_TILE - 1) / lv::RP_TILE > 0x7fffffffLL) { lv::set_error("%s: too many samples", name); return LV_ERR_ARG; }
+    if ((n * B + lv::RP_TILE / 2 - 1) / (lv::RP_TILE / 2) > 0x7fffffffLL) { lv::set_error("%s: too many samples", name); return LV_ERR_ARG; }
     return LV_OK;
 }
 
-template <bool EULER>
-static int reparam_fwd(const char* name, const float* mu, const float* sigma, const float* eps, float* z, float* angles,
-                       float* log_q, int64_t n, int64_t B, int k, void* stream) {
+template <typename T, bool EULER>
+static int reparam_fwd(const char* name, const T* mu, const T* sigma, const T* eps, T* z, T* angles,
+                       T* log_q, int64_t n, int64_t B, int k, void* stream) {
     int rc = reparam_check(name, n, B, k);
     if (rc) return rc;
     const int64_t total = n * B;
     if (total == 0) return LV_OK;
     if (!mu || !sigma || !eps || (EULER ? !angles : !z)) { lv::set_error("%s: null pointer", name); return LV_ERR_ARG; }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const unsigned grid = unsigned((total + lv::RP_TILE - 1) / lv::RP_TILE);
-    if (k == 3) lv::so3_reparam_fwd_kernel<3, EULER><<<grid, lv::RP_TILE, 0, st>>>(mu, sigma, eps, z, angles, log_q, total, B, k);
-    else if (k == 10) lv::so3_reparam_fwd_kernel<10, EULER><<<grid, lv::RP_TILE, 0, st>>>(mu, sigma, eps, z, angles, log_q, total, B, k);
-    else lv::so3_reparam_fwd_kernel<0, EULER><<<grid, lv::RP_TILE, 0, st>>>(mu, sigma, eps, z, angles, log_q, total, B, k);
+    constexpr int TILE = sizeof(T) == 8 ? lv::RP_TILE / 2 : lv::RP_TILE;
+    const unsigned grid = unsigned((total + TILE - 1) / TILE);
+    if (sizeof(T) == 8) lv::so3_reparam_fwd_kernel<T, 0, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, z, angles, log_q, total, B, k);
+    else if (k == 3) lv::so3_reparam_fwd_kernel<T, 3, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, z, angles, log_q, total, B, k);
+    else if (k == 10) lv::so3_reparam_fwd_kernel<T, 10, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, z, angles, log_q, total, B, k);
+    else lv::so3_reparam_fwd_kernel<T, 0, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, z, angles, log_q, total, B, k);
     return lv::check_launch(name);
 }
 
-template <bool EULER>
-static int reparam_bwd(const char* name, const float* mu, const float* sigma, const float* eps, const float* gz,
-                       const float* gangles, const float* glq, float* gmu, float* gsigma, int64_t n, int64_t B, int k,
+template <typename T, bool EULER>
+static int reparam_bwd(const char* name, const T* mu, const T* sigma, const T* eps, const T* gz,
+                       const T* gangles, const T* glq, T* gmu, T* gsigma, int64_t n, int64_t B, int k,
                        void* stream) {
     int rc = reparam_check(name, n, B, k);
     if (rc) return rc;
@@ -314,32 +328,32 @@ static int reparam_bwd(const char* name, const float* mu, const float* sigma, co
     if (total == 0) return LV_OK;
     if (!mu || !sigma || !eps || !gmu || !gsigma || (EULER && !gangles)) { lv::set_error("%s: null pointer", name); return LV_ERR_ARG; }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const unsigned grid = unsigned((total + lv::RP_TILE - 1) / lv::RP_TILE);
-    if (k == 3) lv::so3_reparam_bwd_kernel<3, EULER><<<grid, lv::RP_TILE, 0, st>>>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, total, B, k);
-    else if (k == 10) lv::so3_reparam_bwd_kernel<10, EULER><<<grid, lv::RP_TILE, 0, st>>>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, total, B, k);
-    else lv::so3_reparam_bwd_kernel<0, EULER><<<grid, lv::RP_TILE, 0, st>>>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, total, B, k);
+    constexpr int TILE = sizeof(T) == 8 ? lv::RP_TILE / 2 : lv::RP_TILE;
+    const unsigned grid = unsigned((total + TILE - 1) / TILE);
+    if (sizeof(T) == 8) lv::so3_reparam_bwd_kernel<T, 0, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, total, B, k);
+    else if (k == 3) lv::so3_reparam_bwd_kernel<T, 3, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, total, B, k);
+    else if (k == 10) lv::so3_reparam_bwd_kernel<T, 10, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, total, B, k);
+    else lv::so3_reparam_bwd_kernel<T, 0, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, total, B, k);
     return lv::check_launch(name);
 }
 
-extern "C" int lv_so3_reparam_fwd_f32(const float* mu, const float* sigma, const float* eps, float* z, float* log_q,
-                                      int64_t n, int64_t B, int k, void* stream) {
-    return reparam_fwd<false>("so3_reparam_fwd", mu, sigma, eps, z, nullptr, log_q, n, B, k, stream);
-}
-
-extern "C" int lv_so3_reparam_bwd_f32(const float* mu, const float* sigma, const float* eps, const float* gz,
-                                      const float* glq, float* gmu, float* gsigma, int64_t n, int64_t B, int k,
-                                      void* stream) {
-    return reparam_bwd<false>("so3_reparam_bwd", mu, sigma, eps, gz, nullptr, glq, gmu, gsigma, n, B, k, stream);
-}
-
-// reparameterize fused with matrix -> ZYZ Euler (the pose the action decoder consumes); z is optional
-extern "C" int lv_so3_reparam_eazyz_fwd_f32(const float* mu, const float* sigma, const float* eps, float* z, float* angles,
-                                            float* log_q, int64_t n, int64_t B, int k, void* stream) {
-    return reparam_fwd<true>("so3_reparam_eazyz_fwd", mu, sigma, eps, z, angles, log_q, n, B, k, stream);
-}
-
-extern "C" int lv_so3_reparam_eazyz_bwd_f32(const float* mu, const float* sigma, const float* eps, const float* gz,
-                                            const float* gangles, const float* glq, float* gmu, float* gsigma, int64_t n,
-                                            int64_t B, int k, void* stream) {
-    return reparam_bwd<true>("so3_reparam_eazyz_bwd", mu, sigma, eps, gz, gangles, glq, gmu, gsigma, n, B, k, stream);
-}
+#define LV_REPARAM_ENTRY(SFX, T)                                                                                                 \
+    extern "C" int lv_so3_reparam_fwd_##SFX(const T* mu, const T* sigma, const T* eps, T* z, T* log_q, int64_t n, int64_t B,     \
+                                            int k, void* stream) {                                                               \
+        return reparam_fwd<T, false>("so3_reparam_fwd", mu, sigma, eps, z, nullptr, log_q, n, B, k, stream);                     \
+    }                                                                                                                            \
+    extern "C" int lv_so3_reparam_bwd_##SFX(const T* mu, const T* sigma, const T* eps, const T* gz, const T* glq, T* gmu,        \
+                                            T* gsigma, int64_t n, int64_t B, int k, void* stream) {                              \
+        return reparam_bwd<T, false>("so3_reparam_bwd", mu, sigma, eps, gz, nullptr, glq, gmu, gsigma, n, B, k, stream);         \
+    }                                                                                                                            \
+    /* reparameterize fused with matrix -> ZYZ Euler (the pose the action decoder consumes); z is optional */                    \
+    extern "C" int lv_so3_reparam_eazyz_fwd_##SFX(const T* mu, const T* sigma, const T* eps, T* z, T* angles, T* log_q,          \
+                                                  int64_t n, int64_t B, int k, void* stream) {                                   \
+        return reparam_fwd<T, true>("so3_reparam_eazyz_fwd", mu, sigma, eps, z, angles, log_q, n, B, k, stream);                 \
+    }                                                                                                                            \
+    extern "C" int lv_so3_reparam_eazyz_bwd_##SFX(const T* mu, const T* sigma, const T* eps, const T* gz, const T* gangles,      \
+                                                  const T* glq, T* gmu, T* gsigma, int64_t n, int64_t B, int k, void* stream) {  \
+        return reparam_bwd<T, true>("so3_reparam_eazyz_bwd", mu, sigma, eps, gz, gangles, glq, gmu, gsigma, n, B, k, stream);    \
+    }
+LV_REPARAM_ENTRY(f32, float)
+LV_REPARAM_ENTRY(f64, double)

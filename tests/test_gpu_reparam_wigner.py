@@ -51,6 +51,35 @@ def test_reparam_matches_reference(mods, name):
     as_good_as_ref32(sg.grad, torch.tensor(g["gsigma"]), gsg32, "g_sigma")
 
 
+@pytest.mark.parametrize("name", ["so3_reparam_k3", "so3_reparam_k10", "so3_reparam_n5", "so3_reparam_iwae",
+                                  "so3_reparam_ka6"])
+def test_reparam_f64_matches_reference(mods, name):
+    """The float64 instantiation of the fused kernels against the reference's float64 fixtures (values and
+    gradients), directly and through the Euler-fused variant."""
+    lt, rp, _ = mods
+    g = load_golden(name)
+    k = int(g["k"])
+    d64 = lambda a: torch.tensor(np.asarray(a), dtype=torch.float64, device="cuda")   # noqa: E731
+    tol = dict(rtol=1e-8, atol=1e-9)
+    mu, sg = d64(g["mu"]).requires_grad_(True), d64(g["sigma"]).requires_grad_(True)
+    z, lq = rp.so3_reparameterize(mu, sg, d64(g["eps"]), k)
+    assert z.dtype == torch.float64 and lq.dtype == torch.float64
+    ((z * d64(g["wz"])).sum() + (lq * d64(g["wl"])).sum()).backward()
+    for got, ref, what in ((z, g["z"], "z"), (lq, g["log_q"], "log_q"), (mu.grad, g["gmu"], "g_mu"), (sg.grad, g["gsigma"], "g_sigma")):
+        np.testing.assert_allclose(got.detach().cpu().numpy(), ref, err_msg=what, **tol)
+    # Euler-fused variant == group_matrix_to_eazyz of the plain one, gradients included
+    wa = torch.randn(z.shape[:-2] + (3,), dtype=torch.float64, device="cuda", generator=torch.Generator("cuda").manual_seed(1))
+    mu1, sg1 = d64(g["mu"]).requires_grad_(True), d64(g["sigma"]).requires_grad_(True)
+    ang1, lq1 = rp.so3_reparameterize_eazyz(mu1, sg1, d64(g["eps"]), k)
+    ((ang1 * wa).sum() + (lq1 * d64(g["wl"])).sum()).backward()
+    mu2, sg2 = d64(g["mu"]).requires_grad_(True), d64(g["sigma"]).requires_grad_(True)
+    z2, lq2 = rp.so3_reparameterize(mu2, sg2, d64(g["eps"]), k)
+    ang2 = lt.group_matrix_to_eazyz(z2)
+    ((ang2 * wa).sum() + (lq2 * d64(g["wl"])).sum()).backward()
+    for a, b, what in ((ang1, ang2, "angles"), (mu1.grad, mu2.grad, "g_mu"), (sg1.grad, sg2.grad, "g_sigma")):
+        np.testing.assert_allclose(a.detach().cpu().numpy(), b.detach().cpu().numpy(), rtol=1e-9, atol=1e-9, err_msg=what)
+
+
 @pytest.mark.parametrize("k", [3, 10, 1, 5, 0])
 def test_reparam_large_vs_oracle(mods, k):
     _, rp, _ = mods
