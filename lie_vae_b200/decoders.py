@@ -1,4 +1,5 @@
-"""Action decoder -- drop-in for the reference's ``lie_vae.decoders.ActionNet``."""
+"""Decoders -- drop-in for the reference's ``lie_vae.decoders`` (``ActionNet`` on the sm_100a Wigner kernels;
+``MLPNet``, the group-agnostic baseline, as host-side PyTorch)."""
 import torch
 from torch import nn as nn
 
@@ -59,3 +60,18 @@ class ActionNet(nn.Module):
         if self.mlp:
             item = self.mlp(item)
         return self.deconv(item)
+
+
+class MLPNet(nn.Module):
+    """Baseline decoder of the reference (``decoders.py:64-87``): the flattened group element ((N,9) matrix or (N,3)
+    angles) goes through an MLP to a ((degrees+1)^2 * rep_copies)-vector and then through ``deconv``.  No group
+    action, hence no kernel of this package: plain PyTorch with the reference's layer layout."""
+
+    def __init__(self, degrees, deconv, in_dims=9, rep_copies=10, layers=3, hidden_dims=50, activation=nn.ReLU):
+        super().__init__()
+        matrix_dims = (degrees + 1) ** 2
+        self.mlp = MLP(in_dims, matrix_dims * rep_copies, hidden_dims, layers, activation)
+        self.deconv = deconv
+
+    def forward(self, x, content_data=None):
+        return self.deconv(self.mlp(x.view(x.size(0), -1)))

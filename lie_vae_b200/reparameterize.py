@@ -6,7 +6,9 @@ sm_100a kernel that scales the algebra noise, exponentiates it (Rodrigues),
 left-multiplies by the mean rotation and evaluates the wrapped log-density with
 its 2k+1 winding terms; ``log_posterior()`` returns that kernel's second output.
 The Euclidean (``Nreparameterize``) and vMF (``Sreparameterize``) baselines of the
-reference are outside the SO(3) hot path and are not provided.
+reference (``reparameterize.py:16-97``) are not on the SO(3) hot path; they are kept as
+plain PyTorch modules with the reference's names, attributes and ``state_dict`` keys so that
+``experiments/vae.py:7-9`` imports resolve against this package unchanged.
 """
 import math
 
@@ -17,7 +19,7 @@ import torch.nn.functional as F
 from . import _ops
 from .lie_tools import rodrigues, quaternions_to_group_matrix, s2s1rodrigues, s2s2_gram_schmidt
 
-__all__ = ["N0reparameterize", "AlgebraMean", "QuaternionMean", "S2S1Mean", "S2S2Mean", "SO3reparameterize",
+__all__ = ["Nreparameterize", "Sreparameterize", "N0reparameterize", "AlgebraMean", "QuaternionMean", "S2S1Mean", "S2S2Mean", "SO3reparameterize",
            "so3_reparameterize", "so3_reparameterize_eazyz", "LOG_PRIOR_SO3"]
 
 LOG_PRIOR_SO3 = -math.log(8.0 * math.pi ** 2)   # reparameterize.py:266
@@ -41,6 +43,105 @@ def so3_reparameterize_eazyz(mu, sigma, eps, k=10):
     Differentiable in mu and sigma.
     """
     return _ops.SO3ReparamEazyz.apply(mu, sigma, eps, k)
+
+
+_HALF_LOG_2PI = 0.5 * math.log(2 * math.pi)
+
+
+def _normal_log_prob(z, mean, std):
+    return -((z - mean) ** 2) / (2 * std ** 2) - std.log() - _HALF_LOG_2PI
+
+
+class Nreparameterize(nn.Module):
+    """Diagonal Gaussian latent in R^z_dim (``reparameterize.py:16-55``): the reference's Euclidean baseline.
+    Host-side PyTorch (two Linear heads + softplus); nothing here touches the SO(3) kernels."""
+
+    def __init__(self, input_dim, z_dim):
+        super().__init__()
+        self.input_dim = input_dim
+        self.z_dim = z_dim
+        self.sigma_linear = nn.Linear(input_dim, z_dim)
+        self.mu_linear = nn.Linear(input_dim, z_dim)
+        self.return_means = False
+        self.mu, self.sigma, self.z = None, None, None
+
+    def forward(self, x, n=1):
+        self.mu = self.mu_linear(x)
+        self.sigma = F.softplus(self.sigma_linear(x))
+        self.z = self.nsample(n=n)
+        return self.z
+
+    def kl(self):
+        return -0.5 * torch.sum(1 + 2 * self.sigma.log() - self.mu.pow(2) - self.sigma ** 2, -1)
+
+    def log_posterior(self):
+        return self._log_posterior(self.z)
+
+    def _log_posterior(self, z):
+        return _normal_log_prob(z, self.mu, self.sigma).sum(-1)
+
+    def log_prior(self):
+        return _normal_log_prob(self.z, torch.zeros_like(self.mu), torch.ones_like(self.sigma)).sum(-1)
+
+    def nsample(self, n=1):
+        if self.return_means:
+            return self.mu.expand(n, -1, -1)
+        eps = torch.randn((n,) + tuple(self.mu.shape), dtype=self.mu.dtype, device=self.mu.device)
+        return self.mu + eps * self.sigma
+
+    def deterministic(self):
+        """Set to return means."""
+        self.return_means = True
+
+
+class Sreparameterize(nn.Module):
+    """von Mises-Fisher latent on the sphere (``reparameterize.py:58-97``).  The vMF arithmetic lives in the
+    third-party ``hyperspherical_vae_pytorch`` package (``reparameterize.py:13``), which this package does not
+    restate: the module keeps the reference's surface and raises ``ImportError`` at first use if it is absent."""
+
+    def __init__(self, input_dim, z_dim):
+        super().__init__()
+        self.input_dim = input_dim
+        self.z_dim = z_dim
+        self.k_linear = nn.Linear(input_dim, 1)
+        self.mu_linear = nn.Linear(input_dim, z_dim)
+        self.return_means = False
+        self.mu, self.k, self.z = None, None, None
+
+    @staticmethod
+    def _dists():
+        try:
+            from hyperspherical_vae_pytorch.distributions import VonMisesFisher, HypersphericalUniform
+        except ImportError as e:
+            raise ImportError("Sreparameterize needs the hyperspherical_vae_pytorch package (vMF sampling / entropy), "
+                              "as the reference does (reparameterize.py:13)") from e
+        return VonMisesFisher, HypersphericalUniform
+
+    def forward(self, x, n=1):
+        mu = self.mu_linear(x)
+        self.mu = mu / mu.norm(p=2, dim=-1, keepdim=True)
+        self.k = F.softplus(self.k_linear(x)) + 1
+        self.z = self.nsample(n=n)
+        return self.z
+
+    def kl(self):
+        vmf, unif = self._dists()
+        return -vmf(self.mu, self.k).entropy() + unif(self.z_dim - 1).entropy().to(self.mu.device)
+
+    def log_posterior(self):
+        return self._dists()[0](self.mu, self.k).log_prob(self.z)
+
+    def log_prior(self):
+        return self._dists()[1](self.z_dim - 1).log_prob(self.z)
+
+    def nsample(self, n=1):
+        if self.return_means:
+            return self.mu.expand(n, -1, -1)
+        return self._dists()[0](self.mu, self.k).rsample(n)
+
+    def deterministic(self):
+        """Set to return means."""
+        self.return_means = True
 
 
 class N0reparameterize(nn.Module):

@@ -95,3 +95,31 @@ def test_module_surface_matches_reference():
     with pytest.raises(NotImplementedError):
         dc.ActionNet(33, torch.nn.Sequential())
     assert tuple(lt.j_matrix(3).shape) == (7, 7) and lt.j_matrix(3).dtype == torch.float32
+    # every name experiments/vae.py:5-12 imports from reparameterize / decoders / lie_tools / utils resolves here
+    for mod, names in ((rp, ["SO3reparameterize", "N0reparameterize", "Nreparameterize", "Sreparameterize", "AlgebraMean",
+                             "QuaternionMean", "S2S1Mean", "S2S2Mean"]),
+                       (dc, ["MLPNet", "ActionNet"]),
+                       (lt, ["group_matrix_to_eazyz", "vector_to_eazyz", "quaternions_to_eazyz"])):
+        for name in names:
+            assert hasattr(mod, name), name
+    import lie_vae_b200.utils as ut
+    assert callable(ut.logsumexp)
+    # the Euclidean baseline is host-side PyTorch: same state_dict keys and formulas as reparameterize.py:16-55
+    torch.manual_seed(0)
+    nr = rp.Nreparameterize(5, 3)
+    assert sorted(nr.state_dict()) == ["mu_linear.bias", "mu_linear.weight", "sigma_linear.bias", "sigma_linear.weight"]
+    z = nr(torch.randn(7, 5), n=4)
+    assert tuple(z.shape) == (4, 7, 3) and tuple(nr.kl().shape) == (7,)
+    ref = torch.distributions.Normal(nr.mu, nr.sigma).log_prob(z).sum(-1)
+    assert torch.allclose(nr.log_posterior(), ref, atol=1e-6)
+    ref0 = torch.distributions.Normal(torch.zeros_like(nr.mu), torch.ones_like(nr.sigma)).log_prob(z).sum(-1)
+    assert torch.allclose(nr.log_prior(), ref0, atol=1e-6)
+    nr.deterministic()
+    assert torch.equal(nr.nsample(2)[1], nr.mu)
+    sr = rp.Sreparameterize(5, 3)
+    assert sorted(sr.state_dict()) == ["k_linear.bias", "k_linear.weight", "mu_linear.bias", "mu_linear.weight"]
+    with pytest.raises(ImportError):
+        sr(torch.randn(2, 5))
+    mn = dc.MLPNet(2, torch.nn.Sequential(), in_dims=9, rep_copies=3)
+    assert tuple(mn(torch.randn(4, 3, 3)).shape) == (4, 27)
+    assert [k for k in mn.state_dict()][:2] == ["mlp.0.weight", "mlp.0.bias"]
