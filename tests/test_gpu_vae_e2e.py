@@ -127,3 +127,22 @@ def test_vae_step_matches_oracle(mean_mode, decoder_mode, n, k, dtype):
         assert err <= gtol, "%s: gradient differs by %.3g (scale %.3g)" % (name, err, scale)
         checked += 1
     assert checked >= 8
+
+
+def test_toy_dataset_tensors():
+    """ToyDataset.generate (experiments/datasets.py:142-158) on the GPU kernels against the oracle on the same poses."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from lie_vae_b200.toy import toy_tensors
+    q, h, x = toy_tensors(n=1000, degrees=6, rep_copies=10)
+    assert tuple(q.shape) == (1000, 4) and tuple(x.shape) == (1000, 49, 10) and h.stride(0) == 0
+    assert abs(h[0].norm().item() - 10.0) < 1e-4
+    assert torch.allclose(q.norm(dim=-1), torch.ones(1000, device="cuda"), atol=1e-5)
+    ref = O.block_wigner_matrix_multiply(O.quaternions_to_eazyz(q.double().cpu()), h.double().cpu(), 6)
+    assert (x.double().cpu() - ref).abs().max().item() < 2e-5 * 10
+    # rotations preserve the signal's norm degree by degree
+    for l in range(7):
+        a, b = x[:, l * l:(l + 1) ** 2].norm(dim=1), h[:, l * l:(l + 1) ** 2].norm(dim=1)
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-4)
+    q2, _, x2 = toy_tensors(n=1000, degrees=6, rep_copies=10)
+    assert torch.equal(q, q2) and torch.equal(x, x2)               # seeded like the reference
