@@ -97,6 +97,16 @@ int lv_vector_to_eazyz_bwd_f64(const double* v, const double* ge, double* gv, in
 int lv_sum_leading_f32(const float* in, float* out, int64_t n, int64_t inner, void* stream);
 int lv_sum_leading_f64(const double* in, double* out, int64_t n, int64_t inner, void* stream);
 
+/* ---- log-sum-exp over the leading axis: utils.logsumexp utils.py:4-26 as used by VAE.log_likelihood
+ *   experiments/vae.py:164-171 (importance weights over the n samples).  in (n, inner) -> out (inner);
+ *   backward: gin (n, inner) = gout[j] * exp(in[i,j] - out[j]). ---- */
+int lv_logsumexp_leading_fwd_f32(const float* in, float* out, int64_t n, int64_t inner, void* stream);
+int lv_logsumexp_leading_fwd_f64(const double* in, double* out, int64_t n, int64_t inner, void* stream);
+int lv_logsumexp_leading_bwd_f32(const float* in, const float* out, const float* gout, float* gin, int64_t n, int64_t inner,
+                                 void* stream);
+int lv_logsumexp_leading_bwd_f64(const double* in, const double* out, const double* gout, double* gin, int64_t n,
+                                 int64_t inner, void* stream);
+
 /* ---- fused SO(3) reparameterize + wrapped log-density.
  *   N0reparameterize.nsample reparameterize.py:137-141 (v = eps*sigma, eps explicit),
  *   SO3reparameterize.nsample reparameterize.py:269-273 (z = mu @ rodrigues(v)),

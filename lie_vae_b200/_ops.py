@@ -124,6 +124,37 @@ def sum_leading(t):
     return out.reshape(t.shape[1:])
 
 
+class LogSumExpLeading(Function):
+    """(n, ...) -> (...): log-sum-exp over the first axis, one pass (running max / sum) per column."""
+
+    @staticmethod
+    def forward(ctx, x):
+        dev = _require_cuda(x)
+        sfx = _sfx(x)
+        n = x.shape[0]
+        if n == 0:
+            raise ValueError("logsumexp over an empty axis")
+        flat = x.reshape(n, -1).contiguous()
+        out = torch.empty(flat.shape[1], dtype=x.dtype, device=dev)
+        with torch.cuda.device(dev):
+            _cabi.call("lv_logsumexp_leading_fwd_" + sfx, _cabi.ptr(flat), _cabi.ptr(out), n, flat.shape[1], _stream())
+        ctx.save_for_backward(flat, out)
+        ctx.shape = tuple(x.shape)
+        return out.reshape(x.shape[1:])
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        flat, out = ctx.saved_tensors
+        n, inner = flat.shape
+        g = gout.reshape(-1).contiguous()
+        gin = torch.empty_like(flat)
+        with torch.cuda.device(flat.device):
+            _cabi.call("lv_logsumexp_leading_bwd_" + _sfx(flat), _cabi.ptr(flat), _cabi.ptr(out), _cabi.ptr(g), _cabi.ptr(gin),
+                       n, inner, _stream())
+        return gin.reshape(ctx.shape)
+
+
 # ------------------------------------------------------------------------------ fused SO(3) reparameterize
 class SO3Reparam(Function):
     """(mu (B,3,3), sigma (B,3), eps (n,B,3), k) -> z (n,B,3,3), log_q (n,B).   float32 (production) or float64."""

@@ -325,6 +325,60 @@ __global__ void sum_leading_kernel(const T* __restrict__ in, T* __restrict__ out
     out[j] = acc;
 }
 
+// ------------------------------------------------------------------ log-sum-exp over the leading axis
+// utils.logsumexp (utils.py:4-26) as VAE.log_likelihood uses it (vae.py:164-171: importance weights over the n samples
+// of a datapoint).  in (n, inner) -> out (inner).  A 256-thread CTA owns 32 consecutive columns (coalesced rows) and
+// splits the n rows eight ways; every thread keeps a running (max, sum of exp) pair in ONE pass over its rows, the
+// eight pairs of a column are merged through shared memory.  An all -inf column gives -inf, +inf gives +inf, NaN
+// propagates -- torch semantics.
+template <typename T>
+__device__ __forceinline__ void lse_merge(T& m, T& s, T m2, T s2) {
+    if (m2 > m) { s = s * Sc<T>::exp(m - m2) + s2; m = m2; }
+    else if (m2 == m) s += s2;                                    // also covers m = m2 = +-inf without inf - inf
+    else s += s2 * Sc<T>::exp(m2 - m);
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+logsumexp_leading_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t n, int64_t inner) {
+    __shared__ T sm_m[8][33], sm_s[8][33];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int64_t j = int64_t(blockIdx.x) * 32 + cx;
+    T m = -HUGE_VAL, s = T(0);
+    bool bad = false;                                             // a NaN anywhere in the column
+    if (j < inner)
+        for (int64_t i = ry; i < n; i += 8) {
+            const T x = in[i * inner + j];
+            bad |= (x != x);
+            lse_merge(m, s, x, T(1));
+        }
+    sm_m[ry][cx] = bad ? T(NAN) : m;
+    sm_s[ry][cx] = s;
+    __syncthreads();
+    if (ry == 0 && j < inner) {
+        T mm = sm_m[0][cx], ss = sm_s[0][cx];
+        bool nan = (mm != mm);
+#pragma unroll
+        for (int r = 1; r < 8; ++r) {
+            const T m2 = sm_m[r][cx];
+            nan |= (m2 != m2);
+            if (!nan) lse_merge(mm, ss, m2, sm_s[r][cx]);
+        }
+        out[j] = nan ? T(NAN) : ((mm == T(HUGE_VAL) || mm == -T(HUGE_VAL)) ? mm : mm + Sc<T>::log(ss));
+    }
+}
+// g_in[i,j] = g_out[j] * exp(in[i,j] - out[j])   (softmax weights over the leading axis)
+template <typename T>
+__global__ void __launch_bounds__(256)
+logsumexp_leading_bwd_kernel(const T* __restrict__ in, const T* __restrict__ out, const T* __restrict__ gout,
+                             T* __restrict__ gin, int64_t total, int64_t inner) {
+    const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int64_t j = idx % inner;
+    const T o = out[j];
+    const T w = (o == -T(HUGE_VAL)) ? T(0) : Sc<T>::exp(in[idx] - o);
+    gin[idx] = gout[j] * w;
+}
+
 }  // namespace lv
 
 // ====================================================================== C ABI
@@ -388,6 +442,34 @@ static int sum_leading(const T* in, T* out, int64_t n, int64_t inner, void* st) 
     lv::sum_leading_kernel<T><<<unsigned(blocks), threads, 0, LV_ST(st)>>>(in, out, n, inner);
     return lv::check_launch("sum_leading");
 }
+template <typename T>
+static int logsumexp_leading(const T* in, T* out, int64_t n, int64_t inner, void* st) {
+    if (n <= 0 || inner < 0 || (inner > 0 && (!in || !out))) { lv::set_error("logsumexp_leading: bad arguments"); return LV_ERR_ARG; }
+    if (inner == 0) return LV_OK;
+    const int64_t blocks = (inner + 31) / 32;
+    if (blocks > 0x7fffffffLL) { lv::set_error("logsumexp_leading: too many columns"); return LV_ERR_ARG; }
+    lv::logsumexp_leading_kernel<T><<<unsigned(blocks), 256, 0, LV_ST(st)>>>(in, out, n, inner);
+    return lv::check_launch("logsumexp_leading");
+}
+template <typename T>
+static int logsumexp_leading_bwd(const T* in, const T* out, const T* gout, T* gin, int64_t n, int64_t inner, void* st) {
+    if (n <= 0 || inner < 0 || (inner > 0 && (!in || !out || !gout || !gin))) { lv::set_error("logsumexp_leading_bwd: bad arguments"); return LV_ERR_ARG; }
+    const int64_t total = n * inner;
+    if (total == 0) return LV_OK;
+    const int64_t blocks = (total + 255) / 256;
+    if (blocks > 0x7fffffffLL) { lv::set_error("logsumexp_leading_bwd: too many elements"); return LV_ERR_ARG; }
+    lv::logsumexp_leading_bwd_kernel<T><<<unsigned(blocks), 256, 0, LV_ST(st)>>>(in, out, gout, gin, total, inner);
+    return lv::check_launch("logsumexp_leading_bwd");
+}
+extern "C" int lv_logsumexp_leading_fwd_f32(const float* in, float* out, int64_t n, int64_t inner, void* st) { return logsumexp_leading<float>(in, out, n, inner, st); }
+extern "C" int lv_logsumexp_leading_fwd_f64(const double* in, double* out, int64_t n, int64_t inner, void* st) { return logsumexp_leading<double>(in, out, n, inner, st); }
+extern "C" int lv_logsumexp_leading_bwd_f32(const float* in, const float* out, const float* gout, float* gin, int64_t n, int64_t inner, void* st) {
+    return logsumexp_leading_bwd<float>(in, out, gout, gin, n, inner, st);
+}
+extern "C" int lv_logsumexp_leading_bwd_f64(const double* in, const double* out, const double* gout, double* gin, int64_t n, int64_t inner, void* st) {
+    return logsumexp_leading_bwd<double>(in, out, gout, gin, n, inner, st);
+}
+
 extern "C" int lv_sum_leading_f32(const float* in, float* out, int64_t n, int64_t inner, void* st) {
     return sum_leading<float>(in, out, n, inner, st);
 }

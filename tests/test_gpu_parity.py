@@ -241,3 +241,68 @@ def test_errors(lt):
         lt.wigner_d_matrix(torch.randn(4, 2, device="cuda"), 1)
     with pytest.raises(NotImplementedError):
         lt.wigner_d_matrix(torch.randn(4, 3, device="cuda"), 33)
+
+
+# ----------------------------------------------------------------------- utils.logsumexp / IWAE bound
+def test_logsumexp_matches_reference(lt):
+    import lie_vae_b200.utils as ut
+    g = load_golden("logsumexp")
+    for dtype, rtol, atol in ((torch.float64, 1e-12, 1e-12), (torch.float32, RTOL, ATOL)):
+        for dim, tag in ((1, "dim1"), (0, "dim0")):
+            x = torch.tensor(g["x"], dtype=dtype, device="cuda").requires_grad_(True)
+            out = ut.logsumexp(x, dim)
+            (out * torch.tensor(g["w_" + tag], dtype=dtype, device="cuda")).sum().backward()
+            close(out, g["out_" + tag], rtol, atol, "lse " + tag)
+            close(x.grad, g["gx_" + tag], rtol, atol, "g lse " + tag)
+            assert ut.logsumexp(x, dim, keepdim=True).shape == torch.logsumexp(x, dim, keepdim=True).shape
+        close(ut.logsumexp(torch.tensor(g["x"], dtype=dtype, device="cuda")), g["out_all"], rtol, atol, "lse all")
+
+
+def test_logsumexp_edge_cases_and_sizes(lt):
+    import lie_vae_b200.utils as ut
+    inf = float("inf")
+    x = torch.tensor([[-inf, 0.0, inf, 1.0, float("nan"), -inf, 1000.0],
+                      [-inf, -inf, 3.0, 2.0, 0.0, 5.0, 1000.0],
+                      [-inf, 1.0, 1.0, -1e4, 1.0, -inf, -1000.0]], device="cuda")
+    got, ref = ut.logsumexp(x, 0), torch.logsumexp(x, 0)
+    assert torch.equal(torch.isnan(got), torch.isnan(ref))
+    ok = ~torch.isnan(ref)
+    assert torch.allclose(got[ok], ref[ok], rtol=1e-6, atol=1e-6) and got[0] == -inf and got[2] == inf
+    torch.manual_seed(0)
+    for shape, dim in (((500, 1), 0), ((1, 77), 0), ((9, 1000, 5), 1), ((33, 70000), 0), ((4, 5, 6), -1)):
+        x = (torch.randn(*shape, device="cuda", dtype=torch.float64) * 30).requires_grad_(True)
+        got = ut.logsumexp(x, dim)
+        got.sum().backward()
+        x2 = x.detach().clone().requires_grad_(True)
+        ref = torch.logsumexp(x2, dim)
+        ref.sum().backward()
+        assert torch.allclose(got, ref, rtol=1e-12, atol=1e-12) and torch.allclose(x.grad, x2.grad, rtol=1e-11, atol=1e-13)
+    with pytest.raises(RuntimeError):
+        ut.logsumexp(torch.zeros(3, 3), 0)
+
+
+def test_iwae_log_likelihood_path(lt):
+    """VAE.log_likelihood (vae.py:164-171; main.py:134-143 uses n = 500, B = 1): reparameterize with n samples of one
+    datapoint -> action decoder -> per-sample reconstruction term -> importance-weighted bound, against the oracle."""
+    import lie_vae_b200.reparameterize as rp
+    import lie_vae_b200.decoders as dc
+    import lie_vae_b200.utils as ut
+    torch.manual_seed(1)
+    n, B, L, C, k = 500, 1, 4, 3, 10
+    M = (L + 1) ** 2
+    mu64 = O.random_group_matrices(B, dtype=torch.float64)
+    sg64 = torch.rand(B, 3, dtype=torch.float64) * 0.5 + 0.1
+    eps64 = torch.randn(n, B, 3, dtype=torch.float64)
+    item64, x64 = torch.randn(M, C, dtype=torch.float64), torch.randn(B, M * C, dtype=torch.float64)
+    z, lq = O.so3_reparameterize(mu64, sg64, eps64, k)
+    rec = O.action_net_forward(O.group_matrix_to_eazyz(z.reshape(-1, 3, 3)), item64, L).reshape(n, B, -1)
+    w = -((rec - x64) ** 2).sum(-1) + O.so3_log_prior(z) - lq
+    ref = (O.logsumexp(w, 0) - math.log(n)).mean()
+    zc, lqc = rp.so3_reparameterize(mu64.float().cuda(), sg64.float().cuda(), eps64.float().cuda(), k)
+    net = dc.ActionNet(L, torch.nn.Sequential(), rep_copies=C).cuda()
+    net.item_rep.data = item64.float().cuda()
+    recc = net(lt.group_matrix_to_eazyz(zc.view(-1, 3, 3))).reshape(n, B, -1)
+    log_p_x_z = -((recc - x64.float().cuda()) ** 2).sum(-1)
+    log_p_z = torch.full((n, B), rp.LOG_PRIOR_SO3, dtype=torch.float64, device="cuda")
+    got = ut.iwae_log_likelihood(log_p_x_z, log_p_z, lqc)
+    assert abs(got.item() - ref.item()) < 5e-4 * max(1.0, abs(ref.item())), (got.item(), ref.item())
