@@ -41,6 +41,29 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class _on:
+    """``with _on(dev):`` makes ``dev`` the current CUDA device for a launch.  Unlike ``torch.cuda.device`` it costs one
+    ``current_device()`` query when ``dev`` already is current (the common case: these wrappers are launch-latency
+    bound at BASELINE configs[1] / configs[2] sizes)."""
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, dev):
+        self.idx = dev.index
+        self.prev = None
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if self.idx is not None and cur != self.idx:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+        return False
+
+
 def _rows(t, width):
     """(..., width...) -> contiguous (n, width) view/copy and the leading shape."""
     return t.reshape(-1, width).contiguous()
@@ -75,7 +98,7 @@ def _make_row_op(name, in_shapes, out_shape, bwd_needs_inputs=True):
                 if f.shape[0] != n:
                     raise ValueError("%s: inputs disagree on the batch size" % name)
             out = torch.empty((n, out_w), dtype=inputs[0].dtype, device=dev)
-            with torch.cuda.device(dev):
+            with _on(dev):
                 _cabi.call("lv_%s_fwd_%s" % (name, sfx), *[_cabi.ptr(f) for f in flat], _cabi.ptr(out), n, _stream())
             ctx.save_for_backward(*(flat if bwd_needs_inputs else []))
             ctx.meta = (sfx, n, lead, [t.shape for t in inputs])
@@ -89,7 +112,7 @@ def _make_row_op(name, in_shapes, out_shape, bwd_needs_inputs=True):
             g = gout.reshape(-1, out_w).contiguous()
             dev = g.device
             gins = [torch.empty((n, w), dtype=g.dtype, device=dev) for w in in_w]
-            with torch.cuda.device(dev):
+            with _on(dev):
                 _cabi.call("lv_%s_bwd_%s" % (name, sfx), *[_cabi.ptr(f) for f in flat], _cabi.ptr(g),
                            *[_cabi.ptr(x) for x in gins], n, _stream())
             return tuple(x.reshape(s) for x, s in zip(gins, shapes))
@@ -119,7 +142,7 @@ def sum_leading(t):
         return t[0]
     flat = t.reshape(n, -1).contiguous()
     out = torch.empty(flat.shape[1], dtype=t.dtype, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         _cabi.call("lv_sum_leading_%s" % _sfx(t), _cabi.ptr(flat), _cabi.ptr(out), n, flat.shape[1], _stream())
     return out.reshape(t.shape[1:])
 
@@ -136,7 +159,7 @@ class LogSumExpLeading(Function):
             raise ValueError("logsumexp over an empty axis")
         flat = x.reshape(n, -1).contiguous()
         out = torch.empty(flat.shape[1], dtype=x.dtype, device=dev)
-        with torch.cuda.device(dev):
+        with _on(dev):
             _cabi.call("lv_logsumexp_leading_fwd_" + sfx, _cabi.ptr(flat), _cabi.ptr(out), n, flat.shape[1], _stream())
         ctx.save_for_backward(flat, out)
         ctx.shape = tuple(x.shape)
@@ -149,7 +172,7 @@ class LogSumExpLeading(Function):
         n, inner = flat.shape
         g = gout.reshape(-1).contiguous()
         gin = torch.empty_like(flat)
-        with torch.cuda.device(flat.device):
+        with _on(flat.device):
             _cabi.call("lv_logsumexp_leading_bwd_" + _sfx(flat), _cabi.ptr(flat), _cabi.ptr(out), _cabi.ptr(g), _cabi.ptr(gin),
                        n, inner, _stream())
         return gin.reshape(ctx.shape)
@@ -177,7 +200,7 @@ class SO3Reparam(Function):
         mu_c, sg_c, ep_c = mu.contiguous(), sigma.contiguous(), eps.contiguous()
         z = torch.empty((n, B, 3, 3), dtype=mu.dtype, device=dev)
         log_q = torch.empty((n, B), dtype=mu.dtype, device=dev)
-        with torch.cuda.device(dev):
+        with _on(dev):
             _cabi.call("lv_so3_reparam_fwd_" + sfx, _cabi.ptr(mu_c), _cabi.ptr(sg_c), _cabi.ptr(ep_c), _cabi.ptr(z),
                        _cabi.ptr(log_q), n, B, int(k), _stream())
         ctx.save_for_backward(mu_c, sg_c, ep_c)
@@ -194,7 +217,7 @@ class SO3Reparam(Function):
         glq = None if glq is None else glq.contiguous()
         gmu = torch.empty((n, B, 3, 3), dtype=mu.dtype, device=dev)
         gsg = torch.empty((n, B, 3), dtype=mu.dtype, device=dev)
-        with torch.cuda.device(dev):
+        with _on(dev):
             _cabi.call("lv_so3_reparam_bwd_" + _sfx(mu), _cabi.ptr(mu), _cabi.ptr(sigma), _cabi.ptr(eps), _cabi.ptr(gz),
                        _cabi.ptr(glq), _cabi.ptr(gmu), _cabi.ptr(gsg), n, B, ctx.k, _stream())
         return sum_leading(gmu), sum_leading(gsg), None, None
@@ -225,7 +248,7 @@ class SO3ReparamEazyz(Function):
         mu_c, sg_c, ep_c = mu.contiguous(), sigma.contiguous(), eps.contiguous()
         angles = torch.empty((n, B, 3), dtype=mu.dtype, device=dev)
         log_q = torch.empty((n, B), dtype=mu.dtype, device=dev)
-        with torch.cuda.device(dev):
+        with _on(dev):
             _cabi.call("lv_so3_reparam_eazyz_fwd_" + sfx, _cabi.ptr(mu_c), _cabi.ptr(sg_c), _cabi.ptr(ep_c), None,
                        _cabi.ptr(angles), _cabi.ptr(log_q), n, B, int(k), _stream())
         ctx.save_for_backward(mu_c, sg_c, ep_c)
@@ -242,7 +265,7 @@ class SO3ReparamEazyz(Function):
         glq = None if glq is None else glq.contiguous()
         gmu = torch.empty((n, B, 3, 3), dtype=mu.dtype, device=dev)
         gsg = torch.empty((n, B, 3), dtype=mu.dtype, device=dev)
-        with torch.cuda.device(dev):
+        with _on(dev):
             _cabi.call("lv_so3_reparam_eazyz_bwd_" + _sfx(mu), _cabi.ptr(mu), _cabi.ptr(sigma), _cabi.ptr(eps), None, _cabi.ptr(gang),
                        _cabi.ptr(glq), _cabi.ptr(gmu), _cabi.ptr(gsg), n, B, ctx.k, _stream())
         return sum_leading(gmu), sum_leading(gsg), None, None
@@ -270,7 +293,7 @@ class WignerApply(Function):
         C = spectrum.shape[-1]
         a_c, s_c = angles.contiguous(), spectrum.contiguous()
         out = torch.empty((N, M, C), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _on(dev):
             _cabi.call("lv_wigner_apply_fwd_f32", _cabi.ptr(a_c), _cabi.ptr(s_c), _cabi.ptr(out), N, lmin, lmax, C,
                        int(shared), int(bool(transpose)), _stream())
         ctx.save_for_backward(a_c, s_c)
@@ -286,7 +309,7 @@ class WignerApply(Function):
         g = gout.contiguous()
         gang = torch.empty((N, 3), dtype=torch.float32, device=dev)
         gspec = torch.empty_like(s_c)
-        with torch.cuda.device(dev):
+        with _on(dev):
             ws, nws = None, 0
             if shared:
                 nws = _cabi.lib().lv_wigner_bwd_workspace_floats(N, lmin, lmax, C)
@@ -343,7 +366,7 @@ class WignerApplyGeneric(Function):
         a_c, s_c = angles.contiguous(), spectrum.contiguous()
         jt = _j_table(lmax, angles.dtype, dev)
         out = torch.empty((N, M, C), dtype=angles.dtype, device=dev)
-        with torch.cuda.device(dev):
+        with _on(dev):
             _cabi.call("lv_wigner_generic_fwd_" + sfx, _cabi.ptr(a_c), _cabi.ptr(s_c), _cabi.ptr(jt), _cabi.ptr(out), N, lmin, lmax,
                        C, int(shared), int(bool(transpose)), _stream())
         ctx.save_for_backward(a_c, s_c, jt)
@@ -359,7 +382,7 @@ class WignerApplyGeneric(Function):
         g = gout.contiguous()
         parts = torch.empty((N, C, 3), dtype=a_c.dtype, device=dev)
         gspec = torch.empty((N, M, C), dtype=a_c.dtype, device=dev)
-        with torch.cuda.device(dev):
+        with _on(dev):
             _cabi.call("lv_wigner_generic_bwd_" + sfx, _cabi.ptr(a_c), _cabi.ptr(s_c), _cabi.ptr(jt), _cabi.ptr(g), _cabi.ptr(parts),
                        _cabi.ptr(gspec), N, lmin, lmax, C, int(shared), int(transpose), _stream())
         return parts.sum(1), (gspec.sum(0) if shared else gspec), None, None, None
