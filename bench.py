@@ -275,9 +275,17 @@ def run_ours(args):
     step_obj.enable_kernel_timing(False)
 
     # ---- end to end through the public autograd API, inputs in pinned host memory ------------------
+    # larger micro-batches than the resident pass: a torch.autograd round trip costs ~0.15 ms of CPU time per Function pair,
+    # so the tape-driven path amortises it over 2^20 samples (y / g_y of 3.4 GB each are still far from resident for 2^24)
+    e_micro = max(micro, min(args.e2e_micro, n_loc))
+    while n_loc % e_micro:
+        e_micro //= 2
+    e_n_micro = n_loc // e_micro
+    ratio = e_micro // micro       # the same upstream gradients as the resident pass, laid out for the larger micro-batches
+    gy_e = gy if ratio == 1 else [torch.cat([gy[(ratio * j + r) % NBUF] for r in range(ratio)]) for j in range(NBUF)]
     mu_h, sg_h, ep_h = (t.cpu().pin_memory() for t in (mu, sigma, eps.view(1, n_loc, 3)))
     copy_stream = torch.cuda.Stream(device=dev)
-    stage = [[torch.empty(micro, 3, 3, device=dev), torch.empty(micro, 3, device=dev), torch.empty(1, micro, 3, device=dev)]
+    stage = [[torch.empty(e_micro, 3, 3, device=dev), torch.empty(e_micro, 3, device=dev), torch.empty(1, e_micro, 3, device=dev)]
              for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     freed = [torch.cuda.Event() for _ in range(2)]
@@ -291,7 +299,7 @@ def run_ours(args):
 
         def issue(i):
             b = i % 2
-            sl = slice(i * micro, (i + 1) * micro)
+            sl = slice(i * e_micro, (i + 1) * e_micro)
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(freed[b])
                 stage[b][0].copy_(mu_h[sl], non_blocking=True)
@@ -301,9 +309,9 @@ def run_ours(args):
         for b in range(2):
             freed[b].record(main)
         issue(0)
-        for i in range(n_micro):
+        for i in range(e_n_micro):
             b = i % 2
-            if i + 1 < n_micro:
+            if i + 1 < e_n_micro:
                 issue(i + 1)
             main.wait_event(ready[b])
             m = stage[b][0].requires_grad_(True)
@@ -313,8 +321,8 @@ def run_ours(args):
             yy = _ops.WignerApply.apply(ang, item_p, 0, L_MAX, False)
             # the decoder that would consume y is outside the hot path: its gradient g_y (and g_log_q) is handed
             # to autograd directly, exactly as a downstream module's backward would
-            glq_i = glq[i * micro:(i + 1) * micro]
-            torch.autograd.backward([yy, lq], [gy[i % NBUF].view(micro, M, CHANNELS), glq_i.view(1, micro)])
+            glq_i = glq[i * e_micro:(i + 1) * e_micro]
+            torch.autograd.backward([yy, lq], [gy_e[i % len(gy_e)].view(e_micro, M, CHANNELS), glq_i.view(1, e_micro)])
             loss_acc += torch.dot(lq.detach()[0], glq_i)
             stage[b][0].grad = None
             stage[b][1].grad = None
@@ -370,6 +378,7 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": samples_per_step / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": n_loc * 60, "d2h_bytes_per_step": 4 * (1 + M * CHANNELS),
+                    "micro_batch": e_micro,
                     "api": "so3_reparameterize_eazyz -> WignerApply (torch.autograd), pinned host mu/sigma/eps, double-buffered copies"},
             "gpu_launches": (step_obj.LAUNCHES_PER_MICROBATCH * n_micro + step_obj.LAUNCHES_PER_SHARD) * args.steps,
             "launch_mode": "cuda_graph_replay" if graph is not None else "plain",
@@ -406,6 +415,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--samples", type=int, default=TOTAL_SAMPLES, help="global samples per step")
     ap.add_argument("--micro", type=int, default=MICRO)
+    ap.add_argument("--e2e-micro", type=int, default=1 << 20, help="micro-batch of the autograd-API end-to-end pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="plain launches instead of replaying a CUDA graph of the rank-local step")
     args = ap.parse_args()
