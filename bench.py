@@ -7,7 +7,7 @@
 Workload (BASELINE.json configs[4], the one the metric is quoted on): 2^24 samples in total, sharded
 by batch over the ranks; per sample: fused reparameterize (+ wrapped log-density, k = 3) -> matrix ->
 ZYZ Euler -> Wigner-D action (l <= 8, 10 channels) forward, then the full backward.  One *step* is one
-pass over the rank's shard in micro-batches of 2^18 samples (the 54 GB output never needs to be
+pass over the rank's shard in micro-batches of 2^20 samples (the 54 GB output never needs to be
 resident), followed by the only collective: an NCCL all-reduce of [loss, grad item_rep] (811 floats).
 
 Prints ONE JSON line (rank 0).  `value` = samples/s with inputs resident in HBM; `e2e` = the same
@@ -33,7 +33,7 @@ sys.path.insert(0, ROOT)
 METRIC = "so3_reparam_wignerD_fwd_bwd_samples_per_sec"
 UNIT = "samples/s"
 TOTAL_SAMPLES = 1 << 24
-MICRO = 1 << 18
+MICRO = 1 << 20
 L_MAX, CHANNELS, K_WIND = 8, 10, 3
 FALLBACK_HBM_GBS = 6650.0
 CPU_SAMPLE = 1 << 16        # bounded CPU sample (= BASELINE config 3's batch); a few seconds per step on 16 cores
@@ -156,7 +156,7 @@ def workload_config(n_gpus):
                         "(l<=8, 81-dim, 10 channels), fwd+bwd, batch-sharded",
             "total_samples": TOTAL_SAMPLES, "micro_batch": MICRO, "degrees": L_MAX, "rep_copies": CHANNELS, "k": K_WIND,
             "parallelism": "dp%d" % n_gpus, "collective": "all-reduce of [loss, grad item_rep] (811 f32) per step",
-            "l2": "inputs_exceed_l2 (every micro-batch streams > 1.7 GB; no reuse between timed iterations)"}
+            "l2": "inputs_exceed_l2 (every micro-batch streams > 6.8 GB; no reuse between timed iterations)"}
 
 
 # ------------------------------------------------------------------------------ our arm
@@ -385,8 +385,8 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "wigner_bwd_ws_kernel<10,8> (+ wigner_reduce_partials)", "achieved": kernels[dom]["gbs"], "peak": peak,
                          "unit": "GB/s", "frac": kernels[dom]["frac"],
                          # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture
-                         # profiles/r01_ncu_wigner_v4_summary.txt (852.56 MB + 7.75 MB at 2^18 samples per launch)
-                         "traffic": 860.31e6 * (micro / 262144.0), "peak_source": peak_src,
+                         # profiles/r01_ncu_wigner_v5_summary.txt (3 410.0 MB + 18.2 MB at 2^20 samples per launch)
+                         "traffic": 3428.27e6 * (micro / 1048576.0), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": abytes[dom] * micro},
             "pipeline_roofline": {"bytes_per_sample": 6656, "achieved_gbs": round(value / world * 6656 / 1e9, 1),
                                   "frac": round(value / world * 6656 / 1e9 / peak, 4)},
