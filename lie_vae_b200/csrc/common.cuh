@@ -101,6 +101,55 @@ __device__ __forceinline__ void tile_s2g(T* __restrict__ dst, const T* __restric
     }
 }
 
+// Full-tile variants: element count and thread count are compile-time constants, so the copy loops unroll completely,
+// every piece's offset is an immediate and no 64-bit index arithmetic is left (the run-time-count versions above spend
+// ~40 % of a latent kernel's instructions on loop control and address math).  Same alignment rule as above.
+template <typename T, int COUNT, int NT>
+__device__ __forceinline__ void tile_g2s_full(T* __restrict__ dst, const T* __restrict__ src) {
+    static_assert(sizeof(T) == 4 || sizeof(T) == 8, "4- or 8-byte scalars");
+    constexpr int V = 16 / sizeof(T), NV = COUNT / V, REST32 = (COUNT - NV * V) * int(sizeof(T) / 4);
+    constexpr int N32 = COUNT * int(sizeof(T) / 4);
+    const int tid = threadIdx.x;
+    if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+#pragma unroll
+        for (int k = 0; k < (NV + NT - 1) / NT; ++k) {
+            const int i = tid + k * NT;
+            if ((k + 1) * NT <= NV || i < NV) cp_async16(dst + i * V, src + i * V);
+        }
+        if (REST32 > 0 && tid < REST32)
+            cp_async4(reinterpret_cast<uint32_t*>(dst + NV * V) + tid, reinterpret_cast<const uint32_t*>(src + NV * V) + tid);
+    } else {
+        const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
+        uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+#pragma unroll
+        for (int k = 0; k < (N32 + NT - 1) / NT; ++k) {
+            const int i = tid + k * NT;
+            if ((k + 1) * NT <= N32 || i < N32) cp_async4(d32 + i, s32 + i);
+        }
+    }
+}
+template <typename T, int COUNT, int NT>
+__device__ __forceinline__ void tile_s2g_full(T* __restrict__ dst, const T* __restrict__ src) {
+    constexpr int V = 16 / sizeof(T), NV = COUNT / V, REST = COUNT - NV * V;
+    const int tid = threadIdx.x;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+        const int4* s4 = reinterpret_cast<const int4*>(src);
+        int4* d4 = reinterpret_cast<int4*>(dst);
+#pragma unroll
+        for (int k = 0; k < (NV + NT - 1) / NT; ++k) {
+            const int i = tid + k * NT;
+            if ((k + 1) * NT <= NV || i < NV) d4[i] = s4[i];
+        }
+        if (REST > 0 && tid < REST) dst[NV * V + tid] = src[NV * V + tid];
+    } else {
+#pragma unroll
+        for (int k = 0; k < (COUNT + NT - 1) / NT; ++k) {
+            const int i = tid + k * NT;
+            if ((k + 1) * NT <= COUNT || i < COUNT) dst[i] = src[i];
+        }
+    }
+}
+
 // ---------------------------------------------------------------- 3x3 helpers (row-major r[9])
 // hat(u): [[0,-u2,u1],[u2,0,-u0],[-u1,u0,0]]      (lie_tools.py:17-43)
 // <G, hat(w)> = w . axial(G),  axial(G) = (G21-G12, G02-G20, G10-G01)

@@ -72,9 +72,16 @@ row_kernel(const T* __restrict__ g0, const T* __restrict__ g1, const T* __restri
 
     const int64_t row0 = int64_t(blockIdx.x) * TILE;
     const int rows = int(min(int64_t(TILE), n - row0));
-    if constexpr (Op::I0 > 0) tile_g2s(s0, g0 + row0 * Op::I0, rows * Op::I0);
-    if constexpr (Op::I1 > 0) tile_g2s(s1, g1 + row0 * Op::I1, rows * Op::I1);
-    if constexpr (Op::I2 > 0) tile_g2s(s2, g2 + row0 * Op::I2, rows * Op::I2);
+    const bool full = rows == TILE;       // every CTA but the last: compile-time copy loops
+    if (full) {
+        if constexpr (Op::I0 > 0) tile_g2s_full<T, TILE * Op::I0, TILE>(s0, g0 + row0 * Op::I0);
+        if constexpr (Op::I1 > 0) tile_g2s_full<T, TILE * Op::I1, TILE>(s1, g1 + row0 * Op::I1);
+        if constexpr (Op::I2 > 0) tile_g2s_full<T, TILE * Op::I2, TILE>(s2, g2 + row0 * Op::I2);
+    } else {
+        if constexpr (Op::I0 > 0) tile_g2s(s0, g0 + row0 * Op::I0, rows * Op::I0);
+        if constexpr (Op::I1 > 0) tile_g2s(s1, g1 + row0 * Op::I1, rows * Op::I1);
+        if constexpr (Op::I2 > 0) tile_g2s(s2, g2 + row0 * Op::I2, rows * Op::I2);
+    }
     tile_async_wait();
     __syncthreads();
     const int t = threadIdx.x;
@@ -92,8 +99,13 @@ row_kernel(const T* __restrict__ g0, const T* __restrict__ g1, const T* __restri
         if constexpr (Op::O1 > 0) row_store<T, Op::O1>(t1 + t * Op::O1, o1);
     }
     __syncthreads();
-    if constexpr (Op::O0 > 0) tile_s2g(h0 + row0 * Op::O0, t0, rows * Op::O0);
-    if constexpr (Op::O1 > 0) tile_s2g(h1 + row0 * Op::O1, t1, rows * Op::O1);
+    if (full) {
+        if constexpr (Op::O0 > 0) tile_s2g_full<T, TILE * Op::O0, TILE>(h0 + row0 * Op::O0, t0);
+        if constexpr (Op::O1 > 0) tile_s2g_full<T, TILE * Op::O1, TILE>(h1 + row0 * Op::O1, t1);
+    } else {
+        if constexpr (Op::O0 > 0) tile_s2g(h0 + row0 * Op::O0, t0, rows * Op::O0);
+        if constexpr (Op::O1 > 0) tile_s2g(h1 + row0 * Op::O1, t1, rows * Op::O1);
+    }
 }
 
 template <typename T, typename Op>

@@ -130,13 +130,14 @@ __device__ __forceinline__ void winding_grad(T theta, T a, int krt, T* d1, T* e2
 
 // ------------------------------------------------------------------ staging of broadcast rows
 // rows [i0, i0+rows) of a (n,B,W) view of a (B,W) tensor: contiguous unless the tile wraps.
-template <typename T, int W>
+template <typename T, int W, int TILE>
 __device__ __forceinline__ void stage_bcast(T* __restrict__ dst, const T* __restrict__ src,
                                             int64_t i0, int rows, int64_t B) {
     // n == 1 (the training case): rows are not broadcast and the emulated 64-bit modulo is skipped
     const int64_t b0 = i0 < B ? i0 : i0 % B;
     if (b0 + rows <= B) {
-        tile_g2s(dst, src + b0 * W, rows * W);
+        if (rows == TILE) tile_g2s_full<T, TILE * W, TILE>(dst, src + b0 * W);
+        else tile_g2s(dst, src + b0 * W, rows * W);
     } else {
         for (int idx = threadIdx.x; idx < rows * W; idx += blockDim.x) {
             const int r = idx / W, c = idx - r * W;
@@ -158,9 +159,11 @@ so3_reparam_fwd_kernel(const T* __restrict__ mu, const T* __restrict__ sigma, co
     __shared__ __align__(16) T s_e[TILE * 3];   // eps in, Euler angles out
     const int64_t i0 = int64_t(blockIdx.x) * TILE;
     const int rows = int(min(int64_t(TILE), total - i0));
-    stage_bcast<T, 9>(s_m, mu, i0, rows, B);
-    stage_bcast<T, 3>(s_s, sigma, i0, rows, B);
-    tile_g2s(s_e, eps + i0 * 3, rows * 3);
+    stage_bcast<T, 9, TILE>(s_m, mu, i0, rows, B);
+    stage_bcast<T, 3, TILE>(s_s, sigma, i0, rows, B);
+    const bool full = rows == TILE;       // every CTA but the last: compile-time copy loops
+    if (full) tile_g2s_full<T, TILE * 3, TILE>(s_e, eps + i0 * 3);
+    else tile_g2s(s_e, eps + i0 * 3, rows * 3);
     tile_async_wait();
     __syncthreads();
     const int t = threadIdx.x;
@@ -197,8 +200,13 @@ so3_reparam_fwd_kernel(const T* __restrict__ mu, const T* __restrict__ sigma, co
         }
     }
     __syncthreads();
-    if (z != nullptr) tile_s2g(z + i0 * 9, s_m, rows * 9);
-    if (EULER) tile_s2g(angles + i0 * 3, s_e, rows * 3);
+    if (full) {
+        if (z != nullptr) tile_s2g_full<T, TILE * 9, TILE>(z + i0 * 9, s_m);
+        if (EULER) tile_s2g_full<T, TILE * 3, TILE>(angles + i0 * 3, s_e);
+    } else {
+        if (z != nullptr) tile_s2g(z + i0 * 9, s_m, rows * 9);
+        if (EULER) tile_s2g(angles + i0 * 3, s_e, rows * 3);
+    }
 }
 
 // ------------------------------------------------------------------ backward
@@ -217,11 +225,18 @@ so3_reparam_bwd_kernel(const T* __restrict__ mu, const T* __restrict__ sigma, co
     __shared__ __align__(16) T s_a[EULER ? TILE * 3 : 4];   // g_angles in
     const int64_t i0 = int64_t(blockIdx.x) * TILE;
     const int rows = int(min(int64_t(TILE), total - i0));
-    stage_bcast<T, 9>(s_m, mu, i0, rows, B);
-    stage_bcast<T, 3>(s_s, sigma, i0, rows, B);
-    tile_g2s(s_e, eps + i0 * 3, rows * 3);
-    if (gz != nullptr) tile_g2s(s_g, gz + i0 * 9, rows * 9);
-    if (EULER) tile_g2s(s_a, gangles + i0 * 3, rows * 3);
+    stage_bcast<T, 9, TILE>(s_m, mu, i0, rows, B);
+    stage_bcast<T, 3, TILE>(s_s, sigma, i0, rows, B);
+    const bool full = rows == TILE;
+    if (full) {
+        tile_g2s_full<T, TILE * 3, TILE>(s_e, eps + i0 * 3);
+        if (gz != nullptr) tile_g2s_full<T, TILE * 9, TILE>(s_g, gz + i0 * 9);
+        if (EULER) tile_g2s_full<T, TILE * 3, TILE>(s_a, gangles + i0 * 3);
+    } else {
+        tile_g2s(s_e, eps + i0 * 3, rows * 3);
+        if (gz != nullptr) tile_g2s(s_g, gz + i0 * 9, rows * 9);
+        if (EULER) tile_g2s(s_a, gangles + i0 * 3, rows * 3);
+    }
     tile_async_wait();
     __syncthreads();
     const int t = threadIdx.x;
@@ -286,8 +301,13 @@ so3_reparam_bwd_kernel(const T* __restrict__ mu, const T* __restrict__ sigma, co
         for (int j = 0; j < 3; ++j) s_e[t * 3 + j] = Sc<T>::fma(gv[j], ep[j], gs_direct[j]);
     }
     __syncthreads();
-    tile_s2g(gmu + i0 * 9, s_g, rows * 9);
-    tile_s2g(gsigma + i0 * 3, s_e, rows * 3);
+    if (full) {
+        tile_s2g_full<T, TILE * 9, TILE>(gmu + i0 * 9, s_g);
+        tile_s2g_full<T, TILE * 3, TILE>(gsigma + i0 * 3, s_e);
+    } else {
+        tile_s2g(gmu + i0 * 9, s_g, rows * 9);
+        tile_s2g(gsigma + i0 * 3, s_e, rows * 3);
+    }
 }
 
 }  // namespace lv
@@ -311,7 +331,7 @@ static int reparam_fwd(const char* name, const T* mu, const T* sigma, const T* e
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     constexpr int TILE = sizeof(T) == 8 ? lv::RP_TILE / 2 : lv::RP_TILE;
     const unsigned grid = unsigned((total + TILE - 1) / TILE);
-    if (sizeof(T) == 8) lv::so3_reparam_fwd_kernel<T, 0, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, z, angles, log_q, total, B, k);
+    if constexpr (sizeof(T) == 8) lv::so3_reparam_fwd_kernel<T, 0, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, z, angles, log_q, total, B, k);
     else if (k == 3) lv::so3_reparam_fwd_kernel<T, 3, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, z, angles, log_q, total, B, k);
     else if (k == 10) lv::so3_reparam_fwd_kernel<T, 10, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, z, angles, log_q, total, B, k);
     else lv::so3_reparam_fwd_kernel<T, 0, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, z, angles, log_q, total, B, k);
@@ -330,7 +350,7 @@ static int reparam_bwd(const char* name, const T* mu, const T* sigma, const T* e
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     constexpr int TILE = sizeof(T) == 8 ? lv::RP_TILE / 2 : lv::RP_TILE;
     const unsigned grid = unsigned((total + TILE - 1) / TILE);
-    if (sizeof(T) == 8) lv::so3_reparam_bwd_kernel<T, 0, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, total, B, k);
+    if constexpr (sizeof(T) == 8) lv::so3_reparam_bwd_kernel<T, 0, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, total, B, k);
     else if (k == 3) lv::so3_reparam_bwd_kernel<T, 3, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, total, B, k);
     else if (k == 10) lv::so3_reparam_bwd_kernel<T, 10, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, total, B, k);
     else lv::so3_reparam_bwd_kernel<T, 0, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, total, B, k);
