@@ -250,62 +250,13 @@ template <typename T> struct S2S1Bwd {
     }
 };
 
-template <typename T>
-__device__ __forceinline__ void normalize_clamped_bwd(const T* e, T nrm, T cl, const T* ge, T* gx) {
-    // x -> x / max(|x|, 1e-5): torch.clamp passes the norm's gradient where |x| >= 1e-5
-    if (nrm >= T(1e-5)) {
-        const T d = e[0] * ge[0] + e[1] * ge[1] + e[2] * ge[2];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) gx[i] = (ge[i] - e[i] * d) / cl;
-    } else {
-#pragma unroll
-        for (int i = 0; i < 3; ++i) gx[i] = ge[i] / cl;
-    }
-}
 template <typename T> struct S2S2Fwd {   // lie_tools.py:81-89
     static constexpr int I0 = 3, I1 = 3, I2 = 0, O0 = 9, O1 = 0;
-    static __device__ __forceinline__ void run(const T* v1, const T* v2, const T*, T* R, T*) {
-        const T c1 = Sc<T>::max(Sc<T>::sqrt(v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2]), T(1e-5));
-        T e1[3] = {v1[0] / c1, v1[1] / c1, v1[2] / c1};
-        const T p = e1[0] * v2[0] + e1[1] * v2[1] + e1[2] * v2[2];
-        T u2[3] = {v2[0] - p * e1[0], v2[1] - p * e1[1], v2[2] - p * e1[2]};
-        const T c2 = Sc<T>::max(Sc<T>::sqrt(u2[0] * u2[0] + u2[1] * u2[1] + u2[2] * u2[2]), T(1e-5));
-        T e2[3] = {u2[0] / c2, u2[1] / c2, u2[2] / c2};
-        R[0] = e1[0]; R[1] = e1[1]; R[2] = e1[2];
-        R[3] = e2[0]; R[4] = e2[1]; R[5] = e2[2];
-        R[6] = e1[1] * e2[2] - e1[2] * e2[1];
-        R[7] = e1[2] * e2[0] - e1[0] * e2[2];
-        R[8] = e1[0] * e2[1] - e1[1] * e2[0];
-    }
+    static __device__ __forceinline__ void run(const T* v1, const T* v2, const T*, T* R, T*) { s2s2_fwd(v1, v2, R); }
 };
 template <typename T> struct S2S2Bwd {
     static constexpr int I0 = 3, I1 = 3, I2 = 9, O0 = 3, O1 = 3;
-    static __device__ __forceinline__ void run(const T* v1, const T* v2, const T* G, T* gv1, T* gv2) {
-        const T n1 = Sc<T>::sqrt(v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2]);
-        const T c1 = Sc<T>::max(n1, T(1e-5));
-        T e1[3] = {v1[0] / c1, v1[1] / c1, v1[2] / c1};
-        const T p = e1[0] * v2[0] + e1[1] * v2[1] + e1[2] * v2[2];
-        T u2[3] = {v2[0] - p * e1[0], v2[1] - p * e1[1], v2[2] - p * e1[2]};
-        const T n2 = Sc<T>::sqrt(u2[0] * u2[0] + u2[1] * u2[1] + u2[2] * u2[2]);
-        const T c2 = Sc<T>::max(n2, T(1e-5));
-        T e2[3] = {u2[0] / c2, u2[1] / c2, u2[2] / c2};
-        const T* g1 = G; const T* g2 = G + 3; const T* g3 = G + 6;
-        // e3 = e1 x e2
-        T ge1[3] = {g1[0] + (e2[1] * g3[2] - e2[2] * g3[1]), g1[1] + (e2[2] * g3[0] - e2[0] * g3[2]),
-                    g1[2] + (e2[0] * g3[1] - e2[1] * g3[0])};
-        T ge2[3] = {g2[0] + (g3[1] * e1[2] - g3[2] * e1[1]), g2[1] + (g3[2] * e1[0] - g3[0] * e1[2]),
-                    g2[2] + (g3[0] * e1[1] - g3[1] * e1[0])};
-        T gu2[3];
-        normalize_clamped_bwd(e2, n2, c2, ge2, gu2);
-        // u2 = v2 - p e1, p = e1.v2
-        const T gp = -(gu2[0] * e1[0] + gu2[1] * e1[1] + gu2[2] * e1[2]);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            gv2[i] = gu2[i] + gp * e1[i];
-            ge1[i] += -p * gu2[i] + gp * v2[i];
-        }
-        normalize_clamped_bwd(e1, n1, c1, ge1, gv1);
-    }
+    static __device__ __forceinline__ void run(const T* v1, const T* v2, const T* G, T* gv1, T* gv2) { s2s2_bwd(v1, v2, G, gv1, gv2); }
 };
 template <typename T> struct VecToEazyzFwd {   // lie_tools.py:92-97
     static constexpr int I0 = 3, I1 = 0, I2 = 0, O0 = 3, O1 = 0;

@@ -20,7 +20,7 @@ from . import _ops
 from .lie_tools import rodrigues, quaternions_to_group_matrix, s2s1rodrigues, s2s2_gram_schmidt
 
 __all__ = ["Nreparameterize", "Sreparameterize", "N0reparameterize", "AlgebraMean", "QuaternionMean", "S2S1Mean", "S2S2Mean", "SO3reparameterize",
-           "so3_reparameterize", "so3_reparameterize_eazyz", "LOG_PRIOR_SO3"]
+           "so3_reparameterize", "so3_reparameterize_eazyz", "so3_head_reparameterize", "LOG_PRIOR_SO3"]
 
 LOG_PRIOR_SO3 = -math.log(8.0 * math.pi ** 2)   # reparameterize.py:266
 
@@ -144,6 +144,17 @@ class Sreparameterize(nn.Module):
         self.return_means = True
 
 
+def so3_head_reparameterize(h, weight, bias, eps, mode, k=10, euler=False):
+    """Encoder heads + reparameterize in ONE kernel.
+
+    h (B,Din <= 32) encoder features; ``weight`` ((Dm+3),Din) / ``bias`` (Dm+3) = [mean head; sigma head] with
+    mode 'alg' (Dm = 3, ``AlgebraMean``), 'q' (Dm = 4, ``QuaternionMean``) or 's2s2' (Dm = 6, ``S2S2Mean``); eps (n,B,3).
+    Returns (z (n,B,3,3) -- or its ZYZ Euler angles (n,B,3) with ``euler`` --, log_q (n,B), mu (B,3,3), sigma (B,3)).
+    Differentiable in h, weight and bias.
+    """
+    return _ops.SO3HeadReparam.apply(h, weight, bias, eps, mode, k, euler)
+
+
 class N0reparameterize(nn.Module):
     """Zero-mean Gaussian in the algebra (``reparameterize.py:100-145``)."""
 
@@ -166,12 +177,14 @@ class N0reparameterize(nn.Module):
             return x.new_full((x.shape[0], self.z_dim), float(self.fixed_sigma))
         return F.softplus(self.sigma_linear(x))
 
-    def sample_noise(self, n=1):
-        """Standard-normal noise (n,B,z_dim) for the current sigma; zeros when deterministic."""
-        shape = (n,) + tuple(self.sigma.shape)
+    def sample_noise(self, n=1, like=None):
+        """Standard-normal noise (n,B,z_dim) for the current sigma (or for the batch of ``like`` (B, ...) before sigma
+        exists: the fused-head path samples first); zeros when deterministic."""
+        ref = self.sigma if like is None else like
+        shape = (n, ref.shape[0], self.z_dim)
         if self.return_means:
-            return self.sigma.new_zeros(shape)
-        return torch.randn(shape, dtype=self.sigma.dtype, device=self.sigma.device)
+            return ref.new_zeros(shape)
+        return torch.randn(shape, dtype=ref.dtype, device=ref.device)
 
     def forward(self, x, n=1):
         self.sigma = self.compute_sigma(x)
@@ -275,8 +288,40 @@ class SO3reparameterize(nn.Module):
         self.return_means = False
         self.mu_lie, self.v, self.z = None, None, None
         self._log_q = None
+        # encoder heads (Linear + mean map, Linear + softplus) inside the reparameterize kernel when the mean module
+        # is AlgebraMean / QuaternionMean / S2S2Mean on float32 CUDA features; set False for the unfused launches
+        self.fuse_heads = True
+        self._fused_input = None
+
+    def _fused_head_mode(self, x):
+        """'alg' / 'q' / 's2s2' when the encoder heads can run inside the reparameterize kernel, else None."""
+        mode = {AlgebraMean: "alg", QuaternionMean: "q", S2S2Mean: "s2s2"}.get(type(self.mean_module))
+        rep = self.reparameterize
+        ok = (self.fuse_heads and mode is not None and type(rep) is N0reparameterize and rep.fixed_sigma is None
+              and not self.return_means and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2
+              and x.shape[1] <= _ops.HEAD_MAX_DIN and self.mean_module.map.weight.dtype == torch.float32)
+        return mode if ok else None
+
+    def _forward_fused(self, x, n, mode):
+        rep, mean = self.reparameterize, self.mean_module
+        W = torch.cat([mean.map.weight, rep.sigma_linear.weight], 0)
+        b = torch.cat([mean.map.bias, rep.sigma_linear.bias], 0)
+        rep.sigma = None
+        try:
+            rep.eps = rep.sample_noise(n, like=x)
+        except TypeError:                                   # a user-supplied sample_noise(n) without the keyword
+            rep.eps = rep.sample_noise(n)
+        self.z, self._log_q, self.mu_lie, rep.sigma = _ops.SO3HeadReparam.apply(x, W, b, rep.eps, mode, self.k, False)
+        self._fused_input = (x, mode)                       # nsample() re-runs the heads so that gradients keep flowing
+        self.v = rep.eps * rep.sigma
+        rep.z = self.v
+        return self.z
 
     def forward(self, x, n=1):
+        mode = self._fused_head_mode(x)
+        if mode is not None:
+            return self._forward_fused(x, n, mode)
+        self._fused_input = None
         self.mu_lie = self.mean_module(x)
         rep = self.reparameterize
         rep.sigma = rep.compute_sigma(x)
@@ -292,6 +337,9 @@ class SO3reparameterize(nn.Module):
         """Draw fresh noise for the cached mu / sigma (``reparameterize.py:269-273``)."""
         if self.return_means:
             return self.mu_lie.expand(n, *[-1] * len(self.mu_lie.shape))
+        if getattr(self, "_fused_input", None) is not None:
+            x, mode = self._fused_input
+            return self._forward_fused(x, n, mode)
         rep = self.reparameterize
         rep.eps = rep.sample_noise(n)
         self.v = rep.eps * rep.sigma

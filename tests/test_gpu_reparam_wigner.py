@@ -454,3 +454,93 @@ def test_wigner_backward_accumulate_flag(mods, L, C, N):
     assert (step.g_item - it.grad).abs().max().item() <= 2e-6 * it.grad.abs().max().item()
     step.decode_backward(0, N, item, g, accumulate=False)          # overwrite mode ignores what was there
     assert (step.g_item - it.grad).abs().max().item() <= 2e-6 * it.grad.abs().max().item()
+
+
+# ----------------------------------------------------------------------- encoder heads fused into the reparameterize kernel
+@pytest.mark.parametrize("mode,n,B,Din,k", [("alg", 1, 1000, 10, 10), ("q", 3, 777, 10, 3), ("s2s2", 1, 513, 10, 10),
+                                            ("alg", 2, 64, 32, 5), ("q", 1, 5, 7, 0), ("s2s2", 2, 300, 16, 3)])
+def test_fused_heads_match_unfused_modules(mods, mode, n, B, Din, k):
+    """SO3reparameterize with the heads inside the kernel (the default) against the same module with fuse_heads = False
+    (Linear -> mean map kernel -> softplus -> reparameterize kernel): z, log_q, mu_lie, sigma, kl and the gradients of the
+    features and of every head parameter."""
+    _, rp, _ = mods
+    torch.manual_seed(B + Din)
+    mean_cls = {"alg": rp.AlgebraMean, "q": rp.QuaternionMean, "s2s2": rp.S2S2Mean}[mode]
+    mod = rp.SO3reparameterize(rp.N0reparameterize(Din, 3), mean_cls(Din), k=k).cuda()
+    if mode == "s2s2":
+        mod.mean_module.map.weight.data.uniform_(-1, 1)
+    x0 = torch.randn(B, Din, device="cuda")
+    eps = torch.randn(n, B, 3, device="cuda")
+    wz, wl = torch.randn(n, B, 3, 3, device="cuda"), torch.randn(n, B, device="cuda")
+    res = []
+    for fuse in (True, False):
+        mod.fuse_heads = fuse
+        mod.zero_grad()
+        mod.reparameterize.sample_noise = lambda n_=1, like=None: eps
+        x = x0.clone().requires_grad_(True)
+        z = mod(x, n)
+        assert (mod._fused_input is not None) == fuse
+        ((z * wz).sum() + (mod.log_posterior() * wl).sum() + mod.kl().sum().float()).backward()
+        res.append((z.detach(), mod.log_posterior().detach(), mod.mu_lie.detach(), mod.reparameterize.sigma.detach(), x.grad,
+                    {k_: p.grad.clone() for k_, p in mod.named_parameters()}))
+    (z1, lq1, mu1, sg1, gx1, gp1), (z2, lq2, mu2, sg2, gx2, gp2) = res
+    close(mu1, mu2, 1e-5, 2e-6, "mu")
+    close(sg1, sg2, 1e-5, 1e-6, "sigma")
+    close(z1, z2, 1e-5, 5e-6, "z")
+    assert (lq1 - lq2).abs().max().item() <= 2e-4 * max(1.0, lq2.abs().max().item())
+    for a, b, what in [(gx1, gx2, "g_x")] + [(gp1[k_], gp2[k_], k_) for k_ in gp1]:
+        scale = max(1.0, b.abs().max().item())
+        assert (a - b).abs().max().item() <= 2e-3 * scale, what
+
+
+def test_fused_heads_functional_euler_and_oracle(mods):
+    """so3_head_reparameterize(..., euler=True) against the float64 oracle composition (Linear -> rodrigues, softplus ->
+    reparameterize -> Euler) including the gradients of features, weight and bias."""
+    _, rp, _ = mods
+    torch.manual_seed(9)
+    B, Din, n, k = 700, 10, 2, 3
+    h64 = torch.randn(B, Din, dtype=torch.float64)
+    W64, b64 = torch.randn(6, Din, dtype=torch.float64) * 0.5, torch.randn(6, dtype=torch.float64) * 0.5
+    eps64 = torch.randn(n, B, 3, dtype=torch.float64)
+    wa, wl = torch.randn(n, B, 3, dtype=torch.float64), torch.randn(n, B, dtype=torch.float64)
+
+    def run(dtype, dev):
+        h, W, b = (t.detach().clone().to(dtype).to(dev).requires_grad_(True) for t in (h64, W64, b64))
+        eps = eps64.to(dtype).to(dev)
+        if dev == "cuda":
+            ang, lq, mu, sg = rp.so3_head_reparameterize(h, W, b, eps, "alg", k, euler=True)
+        else:
+            pre = h @ W.t() + b
+            mu, sg = O.rodrigues(pre[:, :3]), torch.nn.functional.softplus(pre[:, 3:])
+            z, lq = O.so3_reparameterize(mu, sg, eps, k)
+            ang = O.group_matrix_to_eazyz(z)
+        ((ang * wa.to(dtype).to(dev)).sum() + (lq * wl.to(dtype).to(dev)).sum()).backward()
+        return [t.detach().double().cpu() for t in (ang, lq, mu, sg, h.grad, W.grad, b.grad)]
+    got, ref, ref32 = run(torch.float32, "cuda"), run(torch.float64, "cpu"), run(torch.float32, "cpu")
+    names = ["angles", "log_q", "mu", "sigma", "g_h", "g_W", "g_b"]
+    for nm, a, b, c in zip(names, got, ref, ref32):
+        if nm in ("mu", "sigma"):
+            close(a, b, 1e-5, 2e-6, nm)
+        else:
+            as_good_as_ref32(a, b, c, nm)
+
+
+def test_fused_heads_nsample_and_fallbacks(mods):
+    _, rp, _ = mods
+    torch.manual_seed(2)
+    mod = rp.SO3reparameterize(rp.N0reparameterize(10, 3), rp.AlgebraMean(10), k=3).cuda()
+    x = torch.randn(40, 10, device="cuda", requires_grad=True)
+    mod(x, 2)
+    z = mod.nsample(4)                                        # fresh noise, gradients still reach the encoder features
+    assert tuple(z.shape) == (4, 40, 3, 3)
+    z.sum().backward()
+    assert x.grad is not None and x.grad.abs().sum().item() > 0 and mod.mean_module.map.weight.grad is not None
+    # paths the fused kernel does not cover fall back to the separate launches: S2S1 mean, fixed sigma, wide features, float64
+    for m2, xin in ((rp.SO3reparameterize(rp.N0reparameterize(10, 3), rp.S2S1Mean(10)).cuda(), torch.randn(8, 10, device="cuda")),
+                    (rp.SO3reparameterize(rp.N0reparameterize(10, 3, fixed_sigma=0.3), rp.AlgebraMean(10)).cuda(), torch.randn(8, 10, device="cuda")),
+                    (rp.SO3reparameterize(rp.N0reparameterize(40, 3), rp.AlgebraMean(40)).cuda(), torch.randn(8, 40, device="cuda")),
+                    (rp.SO3reparameterize(rp.N0reparameterize(10, 3), rp.QuaternionMean(10)).cuda().double(), torch.randn(8, 10, device="cuda", dtype=torch.float64))):
+        out = m2(xin)
+        assert m2._fused_input is None and tuple(out.shape) == (1, 8, 3, 3) and tuple(m2.kl().shape) == (8,)
+    mod.deterministic()
+    assert torch.equal(mod(x)[0], mod.mu_lie)
