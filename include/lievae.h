@@ -140,22 +140,23 @@ int lv_so3_reparam_eazyz_bwd_f64(const double* mu, const double* sigma, const do
                                  int k, void* stream);
 
 /* ---- encoder heads fused into the reparameterize kernels: from encoder features h (B,Din), Din <= 32,
- *   mu    = mean_map(W[:Dm] h + bias[:Dm])     mode 0: rodrigues (AlgebraMean reparameterize.py:148-155, Dm = 3)
+ *   mu    = mean_map(Wm h + bm)                mode 0: rodrigues (AlgebraMean reparameterize.py:148-155, Dm = 3)
  *                                              mode 1: quaternions_to_group_matrix (QuaternionMean :158-164, Dm = 4)
  *                                              mode 2: s2s2_gram_schmidt in float64 (S2S2Mean :184-197, Dm = 6)
- *   sigma = softplus(W[Dm:] h + bias[Dm:])     (N0reparameterize reparameterize.py:117-121)
- *   then exactly lv_so3_reparam(_eazyz)_fwd.  W ((Dm+3), Din) row-major = [mean head; sigma head], bias (Dm+3).
+ *   sigma = softplus(Ws h + bs)                (N0reparameterize reparameterize.py:117-121)
+ *   then exactly lv_so3_reparam(_eazyz)_fwd.  Wm (Dm,Din), bm (Dm), Ws (3,Din), bs (3): the two Linear layers' parameters.
  *   mu (B,9) / sigma (B,3) are optional outputs (module attributes); give `angles` for the Euler-fused variant (z optional).
- *   Backward: gh (n,B,Din) per sample (reduce over n with lv_sum_leading_f32), gWb ((Dm+3), Din+1): row j = the gradient
- *   of W[j,:] followed by the gradient of bias[j], summed over all samples through `workspace`
+ *   Backward: gh (n,B,Din) per sample (reduce over n with lv_sum_leading_f32), gWb ((Dm+3), Din+1): rows of the mean head
+ *   then of the sigma head, each = the gradient of its weight row followed by its bias gradient, summed over all samples through `workspace`
  *   (lv_so3_head_reparam_bwd_workspace_floats floats; deterministic two-pass reduction). ---- */
 int64_t lv_so3_head_reparam_bwd_workspace_floats(int64_t n, int64_t B, int Din, int mode);
-int lv_so3_head_reparam_fwd_f32(const float* h, const float* W, const float* bias, const float* eps, float* mu, float* sigma,
-                                float* z, float* angles, float* log_q, int64_t n, int64_t B, int Din, int mode, int k,
+int lv_so3_head_reparam_fwd_f32(const float* h, const float* Wm, const float* bm, const float* Ws, const float* bs,
+                                const float* eps, float* mu, float* sigma, float* z, float* angles, float* log_q, int64_t n,
+                                int64_t B, int Din, int mode, int k, void* stream);
+int lv_so3_head_reparam_bwd_f32(const float* h, const float* Wm, const float* bm, const float* Ws, const float* bs,
+                                const float* eps, const float* gz, const float* gangles, const float* glq, float* gh, float* gWb,
+                                float* workspace, int64_t workspace_floats, int64_t n, int64_t B, int Din, int mode, int k,
                                 void* stream);
-int lv_so3_head_reparam_bwd_f32(const float* h, const float* W, const float* bias, const float* eps, const float* gz,
-                                const float* gangles, const float* glq, float* gh, float* gWb, float* workspace,
-                                int64_t workspace_floats, int64_t n, int64_t B, int Din, int mode, int k, void* stream);
 
 /* ---- block-diagonal Wigner-D action on a spectrum, degrees lmin..lmax (<= 8), C channels.
  *   block_wigner_matrix_multiply lie_tools.py:226-253, wigner_d_matrix lie_tools.py:211-223,

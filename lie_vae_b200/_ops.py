@@ -276,17 +276,17 @@ HEAD_MAX_DIN = 32
 
 
 class SO3HeadReparam(Function):
-    """(h (B,Din), W ((Dm+3),Din), bias (Dm+3), eps (n,B,3), mode, k, euler) -> (pose, log_q, mu, sigma).
+    """(h (B,Din), Wm (Dm,Din), bm (Dm), Ws (3,Din), bs (3), eps (n,B,3), mode, k, euler) -> (pose, log_q, mu, sigma).
 
-    Encoder heads fused into the reparameterize kernel: mu = mean_map(W[:Dm] h + b[:Dm]), sigma = softplus(W[Dm:] h + b[Dm:]),
-    then the sampler.  ``pose`` is z (n,B,3,3), or its ZYZ Euler angles (n,B,3) with ``euler``.  mu (B,3,3) and sigma (B,3)
+    Encoder heads fused into the reparameterize kernel: mu = mean_map(Wm h + bm), sigma = softplus(Ws h + bs), then the
+    sampler.  ``pose`` is z (n,B,3,3), or its ZYZ Euler angles (n,B,3) with ``euler``.  mu (B,3,3) and sigma (B,3)
     are returned for the modules' attributes and are not differentiable outputs.   float32.
     """
 
     @staticmethod
-    def forward(ctx, h, W, bias, eps, mode, k, euler):
-        dev = _require_cuda(h, W, bias, eps)
-        for t in (h, W, bias, eps):
+    def forward(ctx, h, Wm, bm, Ws, bs, eps, mode, k, euler):
+        dev = _require_cuda(h, Wm, bm, Ws, bs, eps)
+        for t in (h, Wm, bm, Ws, bs, eps):
             if t.dtype != torch.float32:
                 raise TypeError("so3_head_reparameterize is float32 only, got %s" % t.dtype)
         m = HEAD_MODES[mode]
@@ -294,21 +294,22 @@ class SO3HeadReparam(Function):
         if h.dim() != 2 or h.shape[1] > HEAD_MAX_DIN:
             raise ValueError("h must be (B, Din <= %d), got %s" % (HEAD_MAX_DIN, tuple(h.shape)))
         B, Din = h.shape
-        if tuple(W.shape) != (dm + 3, Din) or tuple(bias.shape) != (dm + 3,):
-            raise ValueError("W / bias must be (%d,%d) / (%d,), got %s / %s" % (dm + 3, Din, dm + 3, tuple(W.shape), tuple(bias.shape)))
+        if tuple(Wm.shape) != (dm, Din) or tuple(bm.shape) != (dm,) or tuple(Ws.shape) != (3, Din) or tuple(bs.shape) != (3,):
+            raise ValueError("head parameters must be (%d,%d), (%d,), (3,%d), (3,); got %s %s %s %s"
+                             % (dm, Din, dm, Din, tuple(Wm.shape), tuple(bm.shape), tuple(Ws.shape), tuple(bs.shape)))
         if eps.dim() != 3 or tuple(eps.shape[1:]) != (B, 3):
             raise ValueError("eps must be (n,B,3), got %s" % (tuple(eps.shape),))
         n = eps.shape[0]
-        h_c, W_c, b_c, e_c = h.contiguous(), W.contiguous(), bias.contiguous(), eps.contiguous()
+        saved = tuple(t.contiguous() for t in (h, Wm, bm, Ws, bs, eps))
         f32 = dict(dtype=torch.float32, device=dev)
         mu, sigma = torch.empty((B, 3, 3), **f32), torch.empty((B, 3), **f32)
         pose = torch.empty((n, B, 3) if euler else (n, B, 3, 3), **f32)
         log_q = torch.empty((n, B), **f32)
         with _on(dev):
-            _cabi.call("lv_so3_head_reparam_fwd_f32", _cabi.ptr(h_c), _cabi.ptr(W_c), _cabi.ptr(b_c), _cabi.ptr(e_c), _cabi.ptr(mu),
-                       _cabi.ptr(sigma), None if euler else _cabi.ptr(pose), _cabi.ptr(pose) if euler else None, _cabi.ptr(log_q),
+            _cabi.call("lv_so3_head_reparam_fwd_f32", *[_cabi.ptr(t) for t in saved], _cabi.ptr(mu), _cabi.ptr(sigma),
+                       None if euler else _cabi.ptr(pose), _cabi.ptr(pose) if euler else None, _cabi.ptr(log_q),
                        n, B, Din, m, int(k), _stream())
-        ctx.save_for_backward(h_c, W_c, b_c, e_c)
+        ctx.save_for_backward(*saved)
         ctx.meta = (m, int(k), bool(euler), dm)
         ctx.mark_non_differentiable(mu, sigma)
         return pose, log_q, mu, sigma
@@ -316,13 +317,14 @@ class SO3HeadReparam(Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, gpose, glq, _gmu, _gsigma):
-        h, W, bias, eps = ctx.saved_tensors
+        saved = ctx.saved_tensors
+        h, eps = saved[0], saved[5]
         m, k, euler, dm = ctx.meta
         n, B, Din = eps.shape[0], h.shape[0], h.shape[1]
         dev = h.device
         f32 = dict(dtype=torch.float32, device=dev)
         if gpose is None and glq is None:
-            return torch.zeros_like(h), torch.zeros_like(W), torch.zeros_like(bias), None, None, None, None
+            return tuple(torch.zeros_like(t) for t in saved[:5]) + (None, None, None, None)
         if euler and gpose is None:
             gpose = torch.zeros((n, B, 3), **f32)
         gpose = None if gpose is None else gpose.contiguous()
@@ -332,10 +334,10 @@ class SO3HeadReparam(Function):
         with _on(dev):
             nws = _cabi.lib().lv_so3_head_reparam_bwd_workspace_floats(n, B, Din, m)
             ws = torch.empty(max(nws, 1), **f32)
-            _cabi.call("lv_so3_head_reparam_bwd_f32", _cabi.ptr(h), _cabi.ptr(W), _cabi.ptr(bias), _cabi.ptr(eps),
+            _cabi.call("lv_so3_head_reparam_bwd_f32", *[_cabi.ptr(t) for t in saved],
                        None if euler else _cabi.ptr(gpose), _cabi.ptr(gpose) if euler else None, _cabi.ptr(glq), _cabi.ptr(gh),
                        _cabi.ptr(gwb), _cabi.ptr(ws), nws, n, B, Din, m, k, _stream())
-        return sum_leading(gh), gwb[:, :Din], gwb[:, Din], None, None, None, None
+        return sum_leading(gh), gwb[:dm, :Din], gwb[:dm, Din], gwb[dm:, :Din], gwb[dm:, Din], None, None, None, None
 
 
 # ------------------------------------------------------------------------------ Wigner-D action

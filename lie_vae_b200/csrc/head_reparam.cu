@@ -13,7 +13,8 @@
 // gradients (a (Dm+3) x (Din+1) matrix) are reduced over the CTA's samples in shared memory and over the CTAs by a
 // second tiny kernel (deterministic, no atomics).
 //
-// W is the row-concatenation [mean head; sigma head] ((Dm+3), Din), bias likewise; Din <= 32.
+// The two heads arrive as their own Linear parameters: Wm (Dm, Din), bm (Dm), Ws (3, Din), bs (3); Din <= 32.
+// Inside the kernel they are one ((Dm+3), Din+1) matrix [mean head; sigma head | bias], and so is the gradient gWb.
 #include "common.cuh"
 #include "reparam_core.cuh"
 
@@ -64,11 +65,15 @@ __device__ __forceinline__ void hr_stage_h(float* __restrict__ dst, const float*
         }
     }
 }
-// W ((DT, Din) row-major) and bias (DT) -> s_w[(Din+1)][HR_WPAD]: column d of W in row d, the bias in row Din
-__device__ __forceinline__ void hr_stage_w(float* __restrict__ s_w, const float* __restrict__ W, const float* __restrict__ bias, int DT, int Din) {
+// [Wm; Ws] (row-major) and [bm; bs] -> s_w[(Din+1)][HR_WPAD]: column d of the stacked weight in row d, the bias in row Din
+__device__ __forceinline__ void hr_stage_w(float* __restrict__ s_w, const float* __restrict__ Wm, const float* __restrict__ bm,
+                                           const float* __restrict__ Ws, const float* __restrict__ bs, int DM, int Din) {
     for (int idx = threadIdx.x; idx < (Din + 1) * HR_WPAD; idx += blockDim.x) {
         const int d = idx / HR_WPAD, j = idx - d * HR_WPAD;
-        s_w[idx] = j < DT ? (d < Din ? __ldg(W + j * Din + d) : __ldg(bias + j)) : 0.f;
+        float v = 0.f;
+        if (j < DM) v = d < Din ? __ldg(Wm + j * Din + d) : __ldg(bm + j);
+        else if (j < DM + 3) v = d < Din ? __ldg(Ws + (j - DM) * Din + d) : __ldg(bs + (j - DM));
+        s_w[idx] = v;
     }
 }
 // pre = bias + W h_t   (DT <= 9 outputs; three broadcast 128-bit reads of W^T per input feature)
@@ -95,7 +100,8 @@ __device__ __forceinline__ void hr_linear(const float* __restrict__ s_w, const f
 // ------------------------------------------------------------------ forward
 template <int MODE, int KT, bool EULER>
 __global__ void __launch_bounds__(HR_TILE)
-head_reparam_fwd_kernel(const float* __restrict__ h, const float* __restrict__ W, const float* __restrict__ bias,
+head_reparam_fwd_kernel(const float* __restrict__ h, const float* __restrict__ Wm, const float* __restrict__ bm, const float* __restrict__ Ws,
+                        const float* __restrict__ bs,
                         const float* __restrict__ eps, float* __restrict__ mu, float* __restrict__ sigma, float* __restrict__ z,
                         float* __restrict__ angles, float* __restrict__ log_q, int64_t total, int64_t B, int Din, int krt) {
     constexpr int DM = hr_mean_rows(MODE), DT = DM + 3;
@@ -108,7 +114,7 @@ head_reparam_fwd_kernel(const float* __restrict__ h, const float* __restrict__ W
     const int rows = int(min(int64_t(HR_TILE), total - i0));
     hr_stage_h(s_h, h, i0, rows, B, Din);
     tile_g2s(s_e, eps + i0 * 3, rows * 3);
-    hr_stage_w(s_w, W, bias, DT, Din);
+    hr_stage_w(s_w, Wm, bm, Ws, bs, DM, Din);
     tile_async_wait();
     __syncthreads();
     const int t = threadIdx.x;
@@ -147,7 +153,8 @@ head_reparam_fwd_kernel(const float* __restrict__ h, const float* __restrict__ W
 // [g_W | g_bias] (row j: Din weight gradients then the bias gradient).
 template <int MODE, int KT, bool EULER>
 __global__ void __launch_bounds__(HR_TILE)
-head_reparam_bwd_kernel(const float* __restrict__ h, const float* __restrict__ W, const float* __restrict__ bias,
+head_reparam_bwd_kernel(const float* __restrict__ h, const float* __restrict__ Wm, const float* __restrict__ bm, const float* __restrict__ Ws,
+                        const float* __restrict__ bs,
                         const float* __restrict__ eps, const float* __restrict__ gz, const float* __restrict__ gangles,
                         const float* __restrict__ glq, float* __restrict__ gh, float* __restrict__ partial, int64_t total,
                         int64_t B, int Din, int krt) {
@@ -166,7 +173,7 @@ head_reparam_bwd_kernel(const float* __restrict__ h, const float* __restrict__ W
     tile_g2s(s_e, eps + i0 * 3, rows * 3);
     if (gz != nullptr) tile_g2s(s_g, gz + i0 * 9, rows * 9);
     if (EULER) tile_g2s(s_a, gangles + i0 * 3, rows * 3);
-    hr_stage_w(s_w, W, bias, DT, Din);
+    hr_stage_w(s_w, Wm, bm, Ws, bs, DM, Din);
     tile_async_wait();
     __syncthreads();
     const int t = threadIdx.x;
@@ -251,17 +258,17 @@ static int hr_check(const char* name, int64_t n, int64_t B, int Din, int mode, i
 }
 
 template <int MODE, bool EULER>
-static int hr_launch_fwd(const float* h, const float* W, const float* bias, const float* eps, float* mu, float* sigma, float* z,
+static int hr_launch_fwd(const float* h, const float* Wm, const float* bm, const float* Ws, const float* bs, const float* eps, float* mu, float* sigma, float* z,
                          float* angles, float* log_q, int64_t total, int64_t B, int Din, int k, cudaStream_t st) {
     const unsigned grid = unsigned((total + HR_TILE - 1) / HR_TILE);
     const size_t smem = size_t((Din + 1) * HR_WPAD + HR_TILE * (3 + 9 + Din)) * 4;
-    if (k == 3) head_reparam_fwd_kernel<MODE, 3, EULER><<<grid, HR_TILE, smem, st>>>(h, W, bias, eps, mu, sigma, z, angles, log_q, total, B, Din, k);
-    else if (k == 10) head_reparam_fwd_kernel<MODE, 10, EULER><<<grid, HR_TILE, smem, st>>>(h, W, bias, eps, mu, sigma, z, angles, log_q, total, B, Din, k);
-    else head_reparam_fwd_kernel<MODE, 0, EULER><<<grid, HR_TILE, smem, st>>>(h, W, bias, eps, mu, sigma, z, angles, log_q, total, B, Din, k);
+    if (k == 3) head_reparam_fwd_kernel<MODE, 3, EULER><<<grid, HR_TILE, smem, st>>>(h, Wm, bm, Ws, bs, eps, mu, sigma, z, angles, log_q, total, B, Din, k);
+    else if (k == 10) head_reparam_fwd_kernel<MODE, 10, EULER><<<grid, HR_TILE, smem, st>>>(h, Wm, bm, Ws, bs, eps, mu, sigma, z, angles, log_q, total, B, Din, k);
+    else head_reparam_fwd_kernel<MODE, 0, EULER><<<grid, HR_TILE, smem, st>>>(h, Wm, bm, Ws, bs, eps, mu, sigma, z, angles, log_q, total, B, Din, k);
     return check_launch("so3_head_reparam_fwd");
 }
 template <int MODE, bool EULER, int KT>
-static int hr_launch_bwd_k(const float* h, const float* W, const float* bias, const float* eps, const float* gz, const float* gangles,
+static int hr_launch_bwd_k(const float* h, const float* Wm, const float* bm, const float* Ws, const float* bs, const float* eps, const float* gz, const float* gangles,
                            const float* glq, float* gh, float* partial, int64_t total, int64_t B, int Din, int k, cudaStream_t st) {
     const unsigned grid = unsigned((total + HR_TILE - 1) / HR_TILE);
     const size_t smem = size_t((Din + 1) * HR_WPAD + HR_TILE * (3 + 9 + 3 + HR_WPAD + 2 * Din)) * 4;
@@ -269,15 +276,15 @@ static int hr_launch_bwd_k(const float* h, const float* W, const float* bias, co
         cudaError_t e = cudaFuncSetAttribute(head_reparam_bwd_kernel<MODE, KT, EULER>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess) { set_error("so3_head_reparam_bwd: cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e)); return int(e); }
     }
-    head_reparam_bwd_kernel<MODE, KT, EULER><<<grid, HR_TILE, smem, st>>>(h, W, bias, eps, gz, gangles, glq, gh, partial, total, B, Din, k);
+    head_reparam_bwd_kernel<MODE, KT, EULER><<<grid, HR_TILE, smem, st>>>(h, Wm, bm, Ws, bs, eps, gz, gangles, glq, gh, partial, total, B, Din, k);
     return check_launch("so3_head_reparam_bwd");
 }
 template <int MODE, bool EULER>
-static int hr_launch_bwd(const float* h, const float* W, const float* bias, const float* eps, const float* gz, const float* gangles,
+static int hr_launch_bwd(const float* h, const float* Wm, const float* bm, const float* Ws, const float* bs, const float* eps, const float* gz, const float* gangles,
                          const float* glq, float* gh, float* partial, int64_t total, int64_t B, int Din, int k, cudaStream_t st) {
-    if (k == 3) return hr_launch_bwd_k<MODE, EULER, 3>(h, W, bias, eps, gz, gangles, glq, gh, partial, total, B, Din, k, st);
-    if (k == 10) return hr_launch_bwd_k<MODE, EULER, 10>(h, W, bias, eps, gz, gangles, glq, gh, partial, total, B, Din, k, st);
-    return hr_launch_bwd_k<MODE, EULER, 0>(h, W, bias, eps, gz, gangles, glq, gh, partial, total, B, Din, k, st);
+    if (k == 3) return hr_launch_bwd_k<MODE, EULER, 3>(h, Wm, bm, Ws, bs, eps, gz, gangles, glq, gh, partial, total, B, Din, k, st);
+    if (k == 10) return hr_launch_bwd_k<MODE, EULER, 10>(h, Wm, bm, Ws, bs, eps, gz, gangles, glq, gh, partial, total, B, Din, k, st);
+    return hr_launch_bwd_k<MODE, EULER, 0>(h, Wm, bm, Ws, bs, eps, gz, gangles, glq, gh, partial, total, B, Din, k, st);
 }
 
 }  // namespace lv
@@ -293,19 +300,19 @@ extern "C" int64_t lv_so3_head_reparam_bwd_workspace_floats(int64_t n, int64_t B
     return ((n * B + lv::HR_TILE - 1) / lv::HR_TILE) * int64_t(lv::hr_mean_rows(mode) + 3) * (Din + 1);
 }
 
-extern "C" int lv_so3_head_reparam_fwd_f32(const float* h, const float* W, const float* bias, const float* eps, float* mu,
+extern "C" int lv_so3_head_reparam_fwd_f32(const float* h, const float* Wm, const float* bm, const float* Ws, const float* bs, const float* eps, float* mu,
                                            float* sigma, float* z, float* angles, float* log_q, int64_t n, int64_t B, int Din,
                                            int mode, int k, void* stream) {
     int rc = lv::hr_check("so3_head_reparam_fwd", n, B, Din, mode, k);
     if (rc) return rc;
     const int64_t total = n * B;
     if (total == 0) return LV_OK;
-    if (!h || !W || !bias || !eps || (!z && !angles)) { lv::set_error("so3_head_reparam_fwd: null pointer"); return LV_ERR_ARG; }
+    if (!h || !Wm || !bm || !Ws || !bs || !eps || (!z && !angles)) { lv::set_error("so3_head_reparam_fwd: null pointer"); return LV_ERR_ARG; }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    return HR_DISPATCH(mode, angles != nullptr, hr_launch_fwd, h, W, bias, eps, mu, sigma, z, angles, log_q, total, B, Din, k, st);
+    return HR_DISPATCH(mode, angles != nullptr, hr_launch_fwd, h, Wm, bm, Ws, bs, eps, mu, sigma, z, angles, log_q, total, B, Din, k, st);
 }
 
-extern "C" int lv_so3_head_reparam_bwd_f32(const float* h, const float* W, const float* bias, const float* eps, const float* gz,
+extern "C" int lv_so3_head_reparam_bwd_f32(const float* h, const float* Wm, const float* bm, const float* Ws, const float* bs, const float* eps, const float* gz,
                                            const float* gangles, const float* glq, float* gh, float* gWb, float* workspace,
                                            int64_t workspace_floats, int64_t n, int64_t B, int Din, int mode, int k, void* stream) {
     int rc = lv::hr_check("so3_head_reparam_bwd", n, B, Din, mode, k);
@@ -319,10 +326,10 @@ extern "C" int lv_so3_head_reparam_bwd_f32(const float* h, const float* W, const
         if (e != cudaSuccess) { lv::set_error("so3_head_reparam_bwd: memset: %s", cudaGetErrorString(e)); return int(e); }
         return LV_OK;
     }
-    if (!h || !W || !bias || !eps || !gh || (!gz && !gangles && !glq)) { lv::set_error("so3_head_reparam_bwd: null pointer"); return LV_ERR_ARG; }
+    if (!h || !Wm || !bm || !Ws || !bs || !eps || !gh || (!gz && !gangles && !glq)) { lv::set_error("so3_head_reparam_bwd: null pointer"); return LV_ERR_ARG; }
     const int64_t need = lv_so3_head_reparam_bwd_workspace_floats(n, B, Din, mode);
     if (!workspace || workspace_floats < need) { lv::set_error("so3_head_reparam_bwd: workspace of %lld floats required", (long long)need); return LV_ERR_ARG; }
-    rc = HR_DISPATCH(mode, gangles != nullptr, hr_launch_bwd, h, W, bias, eps, gz, gangles, glq, gh, workspace, total, B, Din, k, st);
+    rc = HR_DISPATCH(mode, gangles != nullptr, hr_launch_bwd, h, Wm, bm, Ws, bs, eps, gz, gangles, glq, gh, workspace, total, B, Din, k, st);
     if (rc) return rc;
     const int64_t nblk = (total + lv::HR_TILE - 1) / lv::HR_TILE;
     lv::head_reduce_partials<<<(NO + 31) / 32, dim3(32, 8), 0, st>>>(workspace, gWb, nblk, NO);

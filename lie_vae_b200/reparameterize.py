@@ -144,15 +144,16 @@ class Sreparameterize(nn.Module):
         self.return_means = True
 
 
-def so3_head_reparameterize(h, weight, bias, eps, mode, k=10, euler=False):
+def so3_head_reparameterize(h, mean_weight, mean_bias, sigma_weight, sigma_bias, eps, mode, k=10, euler=False):
     """Encoder heads + reparameterize in ONE kernel.
 
-    h (B,Din <= 32) encoder features; ``weight`` ((Dm+3),Din) / ``bias`` (Dm+3) = [mean head; sigma head] with
-    mode 'alg' (Dm = 3, ``AlgebraMean``), 'q' (Dm = 4, ``QuaternionMean``) or 's2s2' (Dm = 6, ``S2S2Mean``); eps (n,B,3).
+    h (B,Din <= 32) encoder features; ``mean_weight`` (Dm,Din) / ``mean_bias`` (Dm) the mean head's Linear with
+    mode 'alg' (Dm = 3, ``AlgebraMean``), 'q' (Dm = 4, ``QuaternionMean``) or 's2s2' (Dm = 6, ``S2S2Mean``);
+    ``sigma_weight`` (3,Din) / ``sigma_bias`` (3) the sigma head's; eps (n,B,3).
     Returns (z (n,B,3,3) -- or its ZYZ Euler angles (n,B,3) with ``euler`` --, log_q (n,B), mu (B,3,3), sigma (B,3)).
-    Differentiable in h, weight and bias.
+    Differentiable in h and the four head parameters.
     """
-    return _ops.SO3HeadReparam.apply(h, weight, bias, eps, mode, k, euler)
+    return _ops.SO3HeadReparam.apply(h, mean_weight, mean_bias, sigma_weight, sigma_bias, eps, mode, k, euler)
 
 
 class N0reparameterize(nn.Module):
@@ -304,14 +305,13 @@ class SO3reparameterize(nn.Module):
 
     def _forward_fused(self, x, n, mode):
         rep, mean = self.reparameterize, self.mean_module
-        W = torch.cat([mean.map.weight, rep.sigma_linear.weight], 0)
-        b = torch.cat([mean.map.bias, rep.sigma_linear.bias], 0)
         rep.sigma = None
         try:
             rep.eps = rep.sample_noise(n, like=x)
         except TypeError:                                   # a user-supplied sample_noise(n) without the keyword
             rep.eps = rep.sample_noise(n)
-        self.z, self._log_q, self.mu_lie, rep.sigma = _ops.SO3HeadReparam.apply(x, W, b, rep.eps, mode, self.k, False)
+        self.z, self._log_q, self.mu_lie, rep.sigma = _ops.SO3HeadReparam.apply(
+            x, mean.map.weight, mean.map.bias, rep.sigma_linear.weight, rep.sigma_linear.bias, rep.eps, mode, self.k, False)
         self._fused_input = (x, mode)                       # nsample() re-runs the heads so that gradients keep flowing
         self.v = rep.eps * rep.sigma
         rep.z = self.v

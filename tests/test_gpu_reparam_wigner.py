@@ -508,7 +508,7 @@ def test_fused_heads_functional_euler_and_oracle(mods):
         h, W, b = (t.detach().clone().to(dtype).to(dev).requires_grad_(True) for t in (h64, W64, b64))
         eps = eps64.to(dtype).to(dev)
         if dev == "cuda":
-            ang, lq, mu, sg = rp.so3_head_reparameterize(h, W, b, eps, "alg", k, euler=True)
+            ang, lq, mu, sg = rp.so3_head_reparameterize(h, W[:3], b[:3], W[3:], b[3:], eps, "alg", k, euler=True)
         else:
             pre = h @ W.t() + b
             mu, sg = O.rodrigues(pre[:, :3]), torch.nn.functional.softplus(pre[:, 3:])

@@ -92,6 +92,24 @@ for k in (3, 10):
 del sets, sg_stress
 torch.cuda.empty_cache()
 
+# ---- SO3reparameterize module (AlgebraMean, Din = 10) from encoder features, heads fused into the kernel or not
+for Bm in (1024, 1 << 20):
+    xs = [torch.randn(Bm, 10, device=dev).requires_grad_(True) for _ in range(4)]
+    gzs, glqs = torch.randn(1, Bm, 3, 3, device=dev), torch.randn(1, Bm, device=dev)
+    mod = rp.SO3reparameterize(rp.N0reparameterize(10, 3), rp.AlgebraMean(10), k=10).to(dev)
+    for fuse in (True, False):
+        mod.fuse_heads = fuse
+
+        def step_m(i, mod=mod, xs=xs):
+            x = xs[i % 4]
+            x.grad = None
+            mod.zero_grad(set_to_none=True)
+            z = mod(x)
+            torch.autograd.backward([z, mod.log_posterior()], [gzs, glqs])
+        row("8f-2 SO3reparameterize(AlgebraMean) module fwd+bwd from features, B=%d, k=10, heads %s" % (Bm, "fused" if fuse else "separate launches"),
+            timed(step_m), Bm, 40 + 12 + 36 + 4 + 36 + 4 + 40)
+    del xs, gzs, glqs
+
 # ---- configs[2]: ActionNet(degrees=8, rep_copies=10), N = 65536 (6516 B/sample shared, 16236 per-sample spectrum)
 N, L = 65536, 8
 M = (L + 1) ** 2
