@@ -12,7 +12,7 @@ import lie_vae_b200.lie_tools as lt  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 18
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-L, C = 8, 10
+L, C = int(os.environ.get("LV_L", "8")), 10
 M = (L + 1) ** 2
 dev = torch.device("cuda")
 torch.manual_seed(0)
