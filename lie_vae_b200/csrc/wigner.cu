@@ -337,22 +337,25 @@ __device__ __forceinline__ void tma_load(void* smem_dst, const void* gsrc, uint3
 }
 
 // ------------------------------------------------------------------ backward, shared spectrum, warp-decoupled (sm_100a)
-// Same math as above, no group barriers.  One persistent 512-thread CTA per SM: 15 math warps and one producer warp,
-// four 16-sample tile buffers in a ring (tile q of the CTA lives in buffer q % 4).
+// Same math as above, no group barriers.  One persistent 512-thread CTA per SM: 14 math warps and two producer warps,
+// four (degrees 0..8) or six (0..6) 16-sample tile buffers in a ring (tile q of the CTA lives in buffer q % NB).
 //   * work item = (tile q, slice p): 32 of the tile's 160 (sample, channel) columns.  Math warps pull items in order from a
 //     shared-memory counter, so a warp that runs ahead (the scheduler favours high warp ids; SMSP 3 hosts one math warp
 //     less) simply takes more items -- nobody waits at a barrier for the slowest warp of a group.
-//   * a math warp waits for full[q % 4] (TMA bytes landed + trig table written), runs the backward chain on its 32
-//     columns (spectrum gradient in place, angle-gradient parts to gp), and arrives on empty[q % 4] (count 5).
-//   * the producer warp (warp 15: highest scheduling priority, on the SMSP with a free slot) owns everything else.  For
-//     tile r, in ring order: wait empty -> column sums of the finished tile into 26 registers per lane (this IS the batch
+//   * a math warp waits for full[q % NB] (TMA bytes landed + trig table written), runs the backward chain on its 32
+//     columns (spectrum gradient in place, angle-gradient parts to gp), and arrives on empty[q % NB] (count 5).
+//   * the two producer warps (the last warps of the CTA: highest scheduling priority) own everything else.  For tile r,
+//     in ring order: wait empty -> column sums of the finished tile into 7 float2 registers per lane (this IS the batch
 //     reduction of the item_rep gradient: no atomics, no L2 reduce traffic, fixed order -> bit-reproducible) -> sum the
-//     angle-gradient parts over the 10 channels and store g_angles -> TMA bulk load of tile r + 4 into the buffer (plus an
-//     L2 prefetch of the tile after it) -> write the trig table of tile r + 4, which it computed *before* the wait ->
-//     arrive on full.  The buffer's turnaround is column sums + one load latency; three tiles are being computed meanwhile.
+//     angle-gradient parts over the 10 channels and store g_angles -> TMA bulk load of tile r + NB into the buffer (plus an
+//     L2 prefetch of the tile after it) -> write the trig table of tile r + NB, which they computed *before* the wait
+//     from angles fetched one tile earlier still -> arrive on full.  The buffer's turnaround is column sums + one load
+//     latency; the other NB - 1 tiles are being computed or waiting meanwhile.
 // Requires full 16-sample tiles and 16-byte aligned g_y (the host sends a ragged tail through wigner_bwd_kernel).
 // 14 math warps + 2 producer warps = 16 warps x 128 registers: the whole register file (warps are allocated in fours)
-constexpr int WD_S = 16, WD_BUFS = 4, WD_MATH_WARPS = 14, WD_THREADS = (WD_MATH_WARPS + 2) * 32, WD_SLICES = 5;
+constexpr int WD_S = 16, WD_MATH_WARPS = 14, WD_THREADS = (WD_MATH_WARPS + 2) * 32, WD_SLICES = 5;
+// tile buffers in the ring: as many as shared memory holds (degrees 0..8: 4 x 51.8 KB, degrees 0..6: 6 x 31.4 KB)
+__host__ __device__ constexpr int wd_bufs(int LT) { return LT <= 6 ? 6 : 4; }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
@@ -363,6 +366,7 @@ __global__ void __launch_bounds__(WD_THREADS, 1)
 wigner_bwd_ws_kernel(const float* __restrict__ angles, const float* __restrict__ spectrum, const float* __restrict__ gout,
                      float* __restrict__ gangles, float* __restrict__ partial, int64_t ntiles, int transpose) {
     constexpr int C = CT, M = (LT + 1) * (LT + 1), MC = M * C, COLS = WD_S * C;     // COLS = 160 columns per tile
+    constexpr int WD_BUFS = wd_bufs(LT);
     static_assert(COLS == WD_SLICES * 32, "a tile must split into whole warps");
     static_assert(MC % 2 == 0, "column sums read float2");
     constexpr uint32_t TILE_BYTES = WD_S * MC * 4u;
@@ -393,9 +397,9 @@ wigner_bwd_ws_kernel(const float* __restrict__ angles, const float* __restrict__
             const int64_t q = item / WD_SLICES;
             if (q >= my_tiles) break;
             const int p = item - int(q) * WD_SLICES;
-            const int buf = int(q) & (WD_BUFS - 1);
+            const int buf = int(q % WD_BUFS);
             const int t = p * 32 + lane, s = t / C, c = t - s * C;
-            mbar_wait(full + buf, uint32_t(q >> 2) & 1u);
+            mbar_wait(full + buf, uint32_t(q / WD_BUFS) & 1u);
             AngleAcc acc;
             bwd_unrolled<0, LT, true>(spectrum + c, tiles + buf * WD_S * MC + s * MC + c, C,
                                       reinterpret_cast<const float4*>(trig_all + (buf * WD_S + s) * WG_TRIG_STRIDE), acc);
@@ -432,7 +436,7 @@ wigner_bwd_ws_kernel(const float* __restrict__ angles, const float* __restrict__
             }
         };
         auto issue_load = [&](int64_t j) {      // one lane: first arrival on full + the bulk load; L2 prefetch of the tile after it
-            const int buf = int(j) & (WD_BUFS - 1);
+            const int buf = int(j % WD_BUFS);
             mbar_expect_tx(full + buf, TILE_BYTES);
             tma_load(tiles + buf * WD_S * MC, gout + (first + j * stride) * WD_S * MC, TILE_BYTES, full + buf);
             if (j + 1 < my_tiles)
@@ -452,14 +456,14 @@ wigner_bwd_ws_kernel(const float* __restrict__ angles, const float* __restrict__
         }
         // phi now belongs to tile min(WD_BUFS, my_tiles)
         for (int64_t r = 0; r < my_tiles; ++r) {
-            const int buf = int(r) & (WD_BUFS - 1);
+            const int buf = int(r % WD_BUFS);
             const int64_t jn = r + WD_BUFS;
             if (jn < my_tiles) {
                 const float phi_next = load_phi(jn + 1);
                 trig_fill(tr, phi);
                 phi = phi_next;
             }
-            mbar_wait(empty + buf, uint32_t(r >> 2) & 1u);
+            mbar_wait(empty + buf, uint32_t(r / WD_BUFS) & 1u);
             // batch reduction: column sums of the finished tile, float2 columns pl, pl + 64, ... (rows are 8-byte aligned)
             const float* tile = tiles + buf * WD_S * MC;
             {
@@ -622,7 +626,8 @@ static int launch_bwd_ws(const WgGeom& g, const float* angles, const float* spec
     }
     const int64_t ntiles = N / WD_S, n_full = ntiles * WD_S, n_tail = N - n_full;
     const int grid = int(ntiles < g.sms ? ntiles : g.sms);
-    const size_t smem = size_t(WD_BUFS * WD_S * MC + WD_BUFS * WD_S * WG_TRIG_STRIDE + WD_BUFS * WD_S * C * 3) * 4 + 2 * WD_BUFS * 8 + 16;
+    constexpr int NB = wd_bufs(LT);
+    const size_t smem = size_t(NB * WD_S * MC + NB * WD_S * WG_TRIG_STRIDE + NB * WD_S * C * 3) * 4 + 2 * NB * 8 + 16;
     int rc = opt_in_smem(wigner_bwd_ws_kernel<C, LT>, smem);
     if (rc) return rc;
     float* partial = workspace;      // one row per CTA, then the tail's rows
