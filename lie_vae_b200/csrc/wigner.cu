@@ -171,6 +171,45 @@ __device__ __forceinline__ void bwd_unrolled(const float* srow, float* trow, int
     degree_bwd<L, GLOBAL_SRC>(srow + L * L * C, trow + L * L * C, C, tg, acc);
     if constexpr (L < LT) bwd_unrolled<L + 1, LT, GLOBAL_SRC>(srow, trow, C, tg, acc);
 }
+// Backward of one degree without the forward recompute (shared or per-sample spectrum alike): only the backward chain
+// g_s = D^T g runs; the angle gradients follow from the body-frame generators of the chain D = X(a) J X(b) J X(c),
+//     G_z = X'(0),  G_y = J G_z J,  G_x = [G_z, G_y]          (a representation of so(3); coefficients in wigner_gen.cuh)
+//     D^-1 dD/dc = G_z,   D^-1 dD/db = -sin(c) G_x + cos(c) G_y,   D^-1 dD/da = sin(b) cos(c) G_x + sin(b) sin(c) G_y + cos(b) G_z
+// i.e. d<g, D s>/d(angle) is a 3x3 combination (angle_grads_from_generators) of T_k = <g_s, G_k s>, k = x, y, z, which are
+// sparse bilinear forms of the column's g_s and s.  1 440 instead of 2 140 FMA-pipe cycles per column, one spectrum load
+// instead of two, no w2 kept in registers.
+struct GenAcc {
+    f32x2_t pz = 0ull;
+    float tx = 0.f, ty = 0.f, sz = 0.f;
+    __device__ __forceinline__ float tz() const { return sz + (wg2::plo(pz) + wg2::phi(pz)); }
+};
+template <int L, bool GLOBAL_SRC>
+__device__ __forceinline__ void degree_bwd_gen(const float* src, float* g, int C, const float4* __restrict__ tg, GenAcc& acc) {
+    using D = PDeg<L>;
+    typename D::Vec x, y;
+    D::template load<false>(y, g, C);                // y = g
+    D::template xrot<true>(y, tg);                   // h4 = X(a)^T g
+    D::jmul(y, x);                                   // h3
+    D::template xrot<true>(x, tg + 4);               // h2
+    D::jmul(x, y);                                   // h1
+    D::template xrot<true>(y, tg + 8);               // g_s
+    D::template load<GLOBAL_SRC>(x, src, C);         // x = s
+    D::gdot(y, x, acc.pz, acc.sz);                   // T_z
+    D::gxy_dots(y, x, acc.tx, acc.ty);               // T_x, T_y
+    D::store(y, g, C);
+}
+template <int L, int LT, bool GLOBAL_SRC>
+__device__ __forceinline__ void bwd_gen_unrolled(const float* srow, float* trow, int C, const float4* tg, GenAcc& acc) {
+    degree_bwd_gen<L, GLOBAL_SRC>(srow + L * L * C, trow + L * L * C, C, tg, acc);
+    if constexpr (L < LT) bwd_gen_unrolled<L + 1, LT, GLOBAL_SRC>(srow, trow, C, tg, acc);
+}
+// (T_x, T_y, T_z) and cos / sin of the second and third angle -> gradient of angle `which` (0, 1, 2)
+__device__ __forceinline__ float angle_grad_from_generators(int which, float tx, float ty, float tz, float cb, float sb, float cc, float sc) {
+    if (which == 0) return fmaf(sb, fmaf(cc, tx, sc * ty), cb * tz);
+    if (which == 1) return fmaf(cc, ty, -(sc * tx));
+    return tz;
+}
+
 template <int LT, bool GLOBAL_SRC>
 __device__ __forceinline__ void bwd_degrees(const float* srow, float* trow, int C, const float4* tg, int lmin, int lmax,
                                             AngleAcc& acc) {
@@ -353,7 +392,14 @@ __device__ __forceinline__ void tma_load(void* smem_dst, const void* gsrc, uint3
 //     latency; the other NB - 1 tiles are being computed or waiting meanwhile.
 // Requires full 16-sample tiles and 16-byte aligned g_y (the host sends a ragged tail through wigner_bwd_kernel).
 // 14 math warps + 2 producer warps = 16 warps x 128 registers: the whole register file (warps are allocated in fours)
-constexpr int WD_S = 16, WD_MATH_WARPS = 14, WD_THREADS = (WD_MATH_WARPS + 2) * 32, WD_SLICES = 5;
+#ifndef WD_MATH_WARPS_N
+#define WD_MATH_WARPS_N 11
+#endif
+#ifndef WD_TOTAL_WARPS_N
+#define WD_TOTAL_WARPS_N 16
+#endif
+constexpr int WD_S = 16, WD_MATH_WARPS = WD_MATH_WARPS_N, WD_PROD_WARPS = WD_TOTAL_WARPS_N - WD_MATH_WARPS, WD_THREADS = WD_TOTAL_WARPS_N * 32, WD_SLICES = 5;
+constexpr int WD_PL = WD_PROD_WARPS * 32;       // producer lanes
 // tile buffers in the ring: as many as shared memory holds (degrees 0..8: 4 x 51.8 KB, degrees 0..6: 6 x 31.4 KB)
 __host__ __device__ constexpr int wd_bufs(int LT) { return LT <= 6 ? 6 : 4; }
 
@@ -370,7 +416,7 @@ wigner_bwd_ws_kernel(const float* __restrict__ angles, const float* __restrict__
     static_assert(COLS == WD_SLICES * 32, "a tile must split into whole warps");
     static_assert(MC % 2 == 0, "column sums read float2");
     constexpr uint32_t TILE_BYTES = WD_S * MC * 4u;
-    constexpr int NC2 = MC / 2, KACC = (NC2 + 63) / 64;                             // float2 columns, accumulators per lane
+    constexpr int NC2 = MC / 2, KACC = (NC2 + WD_PL - 1) / WD_PL;                             // float2 columns, accumulators per lane
     extern __shared__ __align__(16) float smem[];
     float* tiles = smem;                                             // [4][16][MC]
     float* trig_all = tiles + WD_BUFS * WD_S * MC;                   // [4][16][52]
@@ -382,7 +428,7 @@ wigner_bwd_ws_kernel(const float* __restrict__ angles, const float* __restrict__
     const int64_t first = blockIdx.x, stride = gridDim.x;
     const int64_t my_tiles = first < ntiles ? (ntiles - first + stride - 1) / stride : 0;
     if (tid == 0) {
-        for (int b = 0; b < WD_BUFS; ++b) { mbar_init(full + b, 3); mbar_init(empty + b, WD_SLICES); }
+        for (int b = 0; b < WD_BUFS; ++b) { mbar_init(full + b, 1 + WD_PROD_WARPS); mbar_init(empty + b, WD_SLICES); }
         *s_next = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -400,14 +446,13 @@ wigner_bwd_ws_kernel(const float* __restrict__ angles, const float* __restrict__
             const int buf = int(q % WD_BUFS);
             const int t = p * 32 + lane, s = t / C, c = t - s * C;
             mbar_wait(full + buf, uint32_t(q / WD_BUFS) & 1u);
-            AngleAcc acc;
-            bwd_unrolled<0, LT, true>(spectrum + c, tiles + buf * WD_S * MC + s * MC + c, C,
-                                      reinterpret_cast<const float4*>(trig_all + (buf * WD_S + s) * WG_TRIG_STRIDE), acc);
-            const float ga = acc.ga(), gb = acc.gb(), gc = acc.gc();
-            float* gp = gp_all + (buf * COLS + t) * 3;
-            gp[0] = transpose ? -gc : ga;
-            gp[1] = transpose ? -gb : gb;
-            gp[2] = transpose ? -ga : gc;
+            GenAcc acc;
+            bwd_gen_unrolled<0, LT, true>(spectrum + c, tiles + buf * WD_S * MC + s * MC + c, C,
+                                          reinterpret_cast<const float4*>(trig_all + (buf * WD_S + s) * WG_TRIG_STRIDE), acc);
+            float* gp = gp_all + (buf * COLS + t) * 3;          // (T_x, T_y, T_z) of this column
+            gp[0] = acc.tx;
+            gp[1] = acc.ty;
+            gp[2] = acc.tz();
             __syncwarp();
             if (lane == 0) mbar_arrive(empty + buf);       // release: the slice's tile and gp writes are visible to the producer
         }
@@ -471,7 +516,7 @@ wigner_bwd_ws_kernel(const float* __restrict__ angles, const float* __restrict__
                 for (int row = 0; row < WD_S; ++row) {
 #pragma unroll
                     for (int k = 0; k < KACC; ++k) {
-                        const int col2 = pl + 64 * k;
+                        const int col2 = pl + WD_PL * k;
                         if (col2 < NC2) {
                             const float2 v = *reinterpret_cast<const float2*>(tile + row * MC + 2 * col2);
                             asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc[k]) : "l"(wg2::pk(v.x, v.y)));
@@ -479,18 +524,23 @@ wigner_bwd_ws_kernel(const float* __restrict__ angles, const float* __restrict__
                     }
                 }
             }
-            // angle gradients: sum the per-column parts over the channels
+            // angle gradients of sample t_ss: T_k summed over the channels, then the body-frame relation for the effective angles
+            // (a', b', c') whose trig table is still in the buffer (it is overwritten after the barrier below); transpose maps
+            // (a', b', c') = (-c, -b, -a) back
             if (trig_lane) {
                 const int64_t n0 = (first + r * stride) * WD_S;
-                const float* gp = gp_all + buf * COLS * 3 + t_ss * C * 3 + t_a;
-                float sum = 0.f;
+                const float* gp = gp_all + buf * COLS * 3 + t_ss * C * 3;
+                float tx = 0.f, ty = 0.f, tz = 0.f;
 #pragma unroll
-                for (int cc = 0; cc < C; ++cc) sum += gp[cc * 3];
-                gangles[n0 * 3 + pl] = sum;
+                for (int cc = 0; cc < C; ++cc) { tx += gp[cc * 3]; ty += gp[cc * 3 + 1]; tz += gp[cc * 3 + 2]; }
+                const float* tr_s = trig_all + (buf * WD_S + t_ss) * WG_TRIG_STRIDE;
+                const float gval = angle_grad_from_generators(transpose ? 2 - t_a : t_a, tx, ty, tz, tr_s[WG_TRIG_ANGLE], tr_s[WG_TRIG_ANGLE + 2],
+                                                              tr_s[2 * WG_TRIG_ANGLE], tr_s[2 * WG_TRIG_ANGLE + 2]);
+                gangles[n0 * 3 + pl] = transpose ? -gval : gval;
             }
             if (jn < my_tiles) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy accesses of the buffer before the bulk write
-                named_bar_sync(1, 64);                                         // both producer warps are done with the buffer
+                named_bar_sync(1, WD_PL);                                         // both producer warps are done with the buffer
                 if (pl == 0) issue_load(jn);
                 trig_store(buf);
                 __syncwarp();
@@ -500,7 +550,7 @@ wigner_bwd_ws_kernel(const float* __restrict__ angles, const float* __restrict__
         float* prow = partial + int64_t(blockIdx.x) * MC;
 #pragma unroll
         for (int k = 0; k < KACC; ++k) {
-            const int col2 = pl + 64 * k;
+            const int col2 = pl + WD_PL * k;
             if (col2 < NC2) *reinterpret_cast<float2*>(prow + 2 * col2) = make_float2(wg2::plo(acc[k]), wg2::phi(acc[k]));
         }
     }

@@ -345,7 +345,8 @@ def test_ws_backward_matches_cp_async_backward(mods, L, N, tr):
         return a.grad, it.grad
     ga1, gi1 = run(g_aligned)
     ga2, gi2 = run(g_unaligned)
-    assert torch.equal(ga1, ga2)                                   # per-sample math is identical
+    # angle gradients: body-frame generator formulation (warp-decoupled kernel) vs forward recompute (cp.async kernel)
+    assert (ga1 - ga2).abs().max().item() <= 2e-5 * max(1.0, ga2.abs().max().item())
     scale = gi2.abs().max().item()
     assert (gi1 - gi2).abs().max().item() <= 2e-6 * scale          # only the summation order differs
     ga1b, gi1b = run(g_aligned)

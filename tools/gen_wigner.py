@@ -173,6 +173,30 @@ def emit(l, ktab):
     elif not d.singles:
         o.append("        (void)as;")
     o.append("    }")
+    # ---- T_x += <g, G_x s>, T_y += <g, G_y s> with the body-frame generators G_y = J G_z J, G_x = [G_z, G_y] of the chain
+    #      (sparse: each row couples a frequency with its neighbours; coefficients as immediates)
+    import numpy as np
+    Gz = np.zeros((n, n))
+    for i in range(n):
+        if i != l:
+            Gz[i, 2 * l - i] = l - i
+    Gy = J @ Gz @ J
+    Gx = Gz @ Gy - Gy @ Gz
+    o.append("    static __device__ __forceinline__ void gxy_dots(const Vec& g, const Vec& s, float& tx, float& ty) {")
+    n_gen = 0
+    for name, G in (("tx", Gx), ("ty", Gy)):
+        for i in range(n):
+            terms = [(j, G[i, j]) for j in range(n) if abs(G[i, j]) > 1e-12]
+            if not terms:
+                continue
+            e = "%s * %s" % (lit(terms[0][1]), d.acc(terms[0][0], "s"))
+            for j, v in terms[1:]:
+                e = "fmaf(%s, %s, %s)" % (lit(v), d.acc(j, "s"), e)
+            o.append("        %s = fmaf(%s, %s, %s);" % (name, d.acc(i, "g"), e, name))
+            n_gen += len(terms) + 1
+    if n_gen == 0:
+        o.append("        (void)g; (void)s; (void)tx; (void)ty;")
+    o.append("    }")
     o.append("};")
     return "\n".join(o), n_f2, n_f1
 

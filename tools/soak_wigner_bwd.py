@@ -37,7 +37,7 @@ for L in (8, 6):
                         gu.copy_(g)
                         a2, it2 = ang.clone().requires_grad_(True), item.clone().requires_grad_(True)
                         _ops.WignerApply.apply(a2, it2, 0, L, tr).backward(gu)
-                        assert torch.equal(a2.grad, a.grad), (L, N, tr)
+                        assert (a2.grad - a.grad).abs().max().item() <= 2e-5 * max(1.0, a.grad.abs().max().item()), (L, N, tr)
                         assert (it2.grad - it.grad).abs().max().item() <= 3e-6 * it.grad.abs().max().item(), (L, N, tr)
                 else:
                     assert torch.equal(a.grad, ref[0]) and torch.equal(it.grad, ref[1]), (L, N, tr, i)
