@@ -29,11 +29,14 @@
 // tile / spectrum access is base + immediate; <CT = 0, LT = -1> is the run-time fallback for
 // any C <= 256 and any 0 <= lmin <= lmax <= 8.
 //
-// Backward (hand-derived; G = d/dphi X(phi) X(phi)^-1 is the pair generator
-// (G w)_i = (l-i) w_{2l-i}):
-//      h4 = X(a)^T g,  h3 = J h4,  h2 = X(b)^T h3,  h1 = J h2,  g_s = X(c)^T h1
-//      g_a = <h4, G w4>,  g_b = <h2, G w2>,  g_c = <g_s, G s>,   w2 = J X(c) s, w4 = J X(b) w2
-// so only w2 and w4 are recomputed from the spectrum; nothing is saved by the forward.
+// Backward (hand-derived).  Only the backward chain runs per column:
+//      h4 = X(a)^T g,  h3 = J h4,  h2 = X(b)^T h3,  h1 = J h2,  g_s = X(c)^T h1          (g_s = D^T g: the spectrum gradient)
+// The angle gradients need no forward intermediates.  X(phi) = exp(phi G_z) with the pair generator (G_z w)_i = (l-i) w_{2l-i};
+// G_y = J G_z J and G_x = [G_z, G_y] complete a representation of so(3), and differentiating D = exp(a G_z) exp(b G_y) exp(c G_z)
+// in the body frame gives
+//      D^-1 dD/dc = G_z,    D^-1 dD/db = -sin(c) G_x + cos(c) G_y,    D^-1 dD/da = sin(b) cos(c) G_x + sin(b) sin(c) G_y + cos(b) G_z
+// so d<g, D s>/d(angle) is a 3x3 combination of T_k = <g_s, G_k s>, k = x, y, z: sparse bilinear forms of the column's g_s and s
+// (coefficients generated as immediates, wigner_gen.cuh).  Nothing is saved by the forward and nothing of it is recomputed.
 // For a shared spectrum (ActionNet.item_rep, decoders.py:53) the per-sample g_s are summed over
 // the batch reproducibly: tiles are assigned to CTAs statically and every CTA adds its tiles' rows
 // in a fixed order (warp-decoupled kernel: the producer warps' register accumulators; cp.async
@@ -101,39 +104,6 @@ __device__ __forceinline__ void degree_fwd(const float* src, float* dst, int C, 
     D::store(x, dst, C);
 }
 
-// angle-gradient accumulators: one packed pair (summed over its lanes at the end) and one scalar per angle
-struct AngleAcc {
-    f32x2_t pa = 0ull, pb = 0ull, pc = 0ull;
-    float sa = 0.f, sb = 0.f, sc = 0.f;
-    __device__ __forceinline__ float ga() const { return sa + (wg2::plo(pa) + wg2::phi(pa)); }
-    __device__ __forceinline__ float gb() const { return sb + (wg2::plo(pb) + wg2::phi(pb)); }
-    __device__ __forceinline__ float gc() const { return sc + (wg2::plo(pc) + wg2::phi(pc)); }
-};
-
-// g (smem tile column): upstream gradient in, spectrum gradient out (in place).
-template <int L, bool GLOBAL_SRC>
-__device__ __forceinline__ void degree_bwd(const float* src, float* g, int C, const float4* __restrict__ tg, AngleAcc& acc) {
-    using D = PDeg<L>;
-    typename D::Vec x, y, w2;
-    D::template load<GLOBAL_SRC>(x, src, C);
-    D::template xrot<false>(x, tg + 8);
-    D::jmul(x, w2);
-    y = w2;
-    D::template xrot<false>(y, tg + 4);
-    D::jmul(y, x);                                   // x = w4
-    D::template load<false>(y, g, C);                // y = g
-    D::template xrot<true>(y, tg);                   // h4
-    D::gdot(y, x, acc.pa, acc.sa);
-    D::jmul(y, x);                                   // x = h3
-    D::template xrot<true>(x, tg + 4);               // h2
-    D::gdot(x, w2, acc.pb, acc.sb);
-    D::jmul(x, y);                                   // y = h1
-    D::template xrot<true>(y, tg + 8);               // g_s
-    D::template load<GLOBAL_SRC>(x, src, C);
-    D::gdot(y, x, acc.pc, acc.sc);
-    D::store(y, g, C);
-}
-
 #define WG_SWITCH(l, CALL)                      \
     switch (l) {                                \
         case 0: { constexpr int L = 0; CALL; } break; \
@@ -165,11 +135,6 @@ __device__ __forceinline__ void fwd_degrees(const float* srow, float* trow, int 
             off += (2 * l + 1) * C;
         }
     }
-}
-template <int L, int LT, bool GLOBAL_SRC>
-__device__ __forceinline__ void bwd_unrolled(const float* srow, float* trow, int C, const float4* tg, AngleAcc& acc) {
-    degree_bwd<L, GLOBAL_SRC>(srow + L * L * C, trow + L * L * C, C, tg, acc);
-    if constexpr (L < LT) bwd_unrolled<L + 1, LT, GLOBAL_SRC>(srow, trow, C, tg, acc);
 }
 // Backward of one degree without the forward recompute (shared or per-sample spectrum alike): only the backward chain
 // g_s = D^T g runs; the angle gradients follow from the body-frame generators of the chain D = X(a) J X(b) J X(c),
@@ -212,13 +177,13 @@ __device__ __forceinline__ float angle_grad_from_generators(int which, float tx,
 
 template <int LT, bool GLOBAL_SRC>
 __device__ __forceinline__ void bwd_degrees(const float* srow, float* trow, int C, const float4* tg, int lmin, int lmax,
-                                            AngleAcc& acc) {
+                                            GenAcc& acc) {
     if constexpr (LT >= 0) {
-        bwd_unrolled<0, LT, GLOBAL_SRC>(srow, trow, C, tg, acc);
+        bwd_gen_unrolled<0, LT, GLOBAL_SRC>(srow, trow, C, tg, acc);
     } else {
         int off = 0;
         for (int l = lmin; l <= lmax; ++l) {
-            WG_SWITCH(l, (degree_bwd<L, GLOBAL_SRC>(srow + off, trow + off, C, tg, acc)));
+            WG_SWITCH(l, (degree_bwd_gen<L, GLOBAL_SRC>(srow + off, trow + off, C, tg, acc)));
             off += (2 * l + 1) * C;
         }
     }
@@ -309,13 +274,11 @@ wigner_bwd_kernel(const float* __restrict__ angles, const float* __restrict__ sp
             const float4* tg = reinterpret_cast<const float4*>(s_trig + s * WG_TRIG_STRIDE);
             float* trow = tile + s * MC + c;
             const float* srow = SHARED ? s_item + c : spectrum + (n0 + s) * MC + c;
-            AngleAcc acc;
+            GenAcc acc;
             bwd_degrees<LT, !SHARED>(srow, trow, C, tg, lmin, lmax, acc);
-            const float ga = acc.ga(), gb = acc.gb(), gc = acc.gc();
-            // effective angles (a',b',c') = transpose ? (-c,-b,-a) : (a,b,c)
-            s_gp[t * 3 + 0] = transpose ? -gc : ga;
-            s_gp[t * 3 + 1] = transpose ? -gb : gb;
-            s_gp[t * 3 + 2] = transpose ? -ga : gc;
+            s_gp[t * 3 + 0] = acc.tx;            // (T_x, T_y, T_z) of this column
+            s_gp[t * 3 + 1] = acc.ty;
+            s_gp[t * 3 + 2] = acc.tz();
         }
         __syncthreads();
         if (SHARED) {
@@ -348,10 +311,18 @@ wigner_bwd_kernel(const float* __restrict__ angles, const float* __restrict__ sp
             tile_s2g(gspectrum + n0 * MC, tile, rows * MC);
         }
         for (int j = t; j < rows * 3; j += blockDim.x) {
+            // T_k summed over the channels, then the body-frame relation for the effective angles (a',b',c') = transpose ?
+            // (-c,-b,-a) : (a,b,c), whose cos / sin are in the trig table
             const int ss = j / 3, a = j - 3 * ss;
-            float acc = 0.f;
-            for (int cc = 0; cc < C; ++cc) acc += s_gp[(ss * C + cc) * 3 + a];
-            gangles[n0 * 3 + j] = acc;
+            float tx = 0.f, ty = 0.f, tz = 0.f;
+            for (int cc = 0; cc < C; ++cc) {
+                const float* gp = s_gp + (ss * C + cc) * 3;
+                tx += gp[0]; ty += gp[1]; tz += gp[2];
+            }
+            const float* tr_s = s_trig + ss * WG_TRIG_STRIDE;
+            const float gval = angle_grad_from_generators(transpose ? 2 - a : a, tx, ty, tz, tr_s[WG_TRIG_ANGLE], tr_s[WG_TRIG_ANGLE + 2],
+                                                          tr_s[2 * WG_TRIG_ANGLE], tr_s[2 * WG_TRIG_ANGLE + 2]);
+            gangles[n0 * 3 + j] = transpose ? -gval : gval;
         }
         __syncthreads();
     }
@@ -524,9 +495,15 @@ wigner_bwd_ws_kernel(const float* __restrict__ angles, const float* __restrict__
                     }
                 }
             }
+            // the buffer is free as soon as every producer warp has summed its columns: refill it first, the angle gradients
+            // (which read only gp and the trig table) follow off the load's critical path
+            if (jn < my_tiles) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy accesses of the buffer before the bulk write
+                named_bar_sync(1, WD_PL);                                      // all producer warps are done with the buffer
+                if (pl == 0) issue_load(jn);
+            }
             // angle gradients of sample t_ss: T_k summed over the channels, then the body-frame relation for the effective angles
-            // (a', b', c') whose trig table is still in the buffer (it is overwritten after the barrier below); transpose maps
-            // (a', b', c') = (-c, -b, -a) back
+            // (a', b', c') whose trig table is still in the buffer; transpose maps (a', b', c') = (-c, -b, -a) back
             if (trig_lane) {
                 const int64_t n0 = (first + r * stride) * WD_S;
                 const float* gp = gp_all + buf * COLS * 3 + t_ss * C * 3;
@@ -539,9 +516,7 @@ wigner_bwd_ws_kernel(const float* __restrict__ angles, const float* __restrict__
                 gangles[n0 * 3 + pl] = transpose ? -gval : gval;
             }
             if (jn < my_tiles) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy accesses of the buffer before the bulk write
-                named_bar_sync(1, WD_PL);                                         // both producer warps are done with the buffer
-                if (pl == 0) issue_load(jn);
+                if (pw < 2) named_bar_sync(2, 64);     // the 48 trig lanes sit in producer warps 0 and 1: old table read before it is replaced
                 trig_store(buf);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(full + buf);
