@@ -385,8 +385,8 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "wigner_bwd_ws_kernel<10,8> (+ wigner_reduce_partials)", "achieved": kernels[dom]["gbs"], "peak": peak,
                          "unit": "GB/s", "frac": kernels[dom]["frac"],
                          # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture
-                         # profiles/r01_ncu_wigner_v5_summary.txt (3 410.0 MB + 18.2 MB at 2^20 samples per launch)
-                         "traffic": 3428.27e6 * (micro / 1048576.0), "peak_source": peak_src,
+                         # profiles/r01_ncu_wigner_v6_summary.txt (3 410.0 MB + 18.8 MB at 2^20 samples per launch)
+                         "traffic": 3428.85e6 * (micro / 1048576.0), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": abytes[dom] * micro},
             "pipeline_roofline": {"bytes_per_sample": 6656, "achieved_gbs": round(value / world * 6656 / 1e9, 1),
                                   "frac": round(value / world * 6656 / 1e9 / peak, 4)},
