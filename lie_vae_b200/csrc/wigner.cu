@@ -19,7 +19,7 @@
 //             store (cp.async.bulk.global.shared::cta) issued by one thread -- no per-thread
 //             copy-out loop, the LSU and the issue slots stay with the math;
 //   backward: (shared spectrum, the ActionNet case) one persistent CTA per SM: math warps pull
-//             32-column slices of TMA-loaded tiles from a work counter, two producer warps recycle
+//             32-column slices of TMA-loaded tiles from a work counter, five producer warps recycle
 //             the four tile buffers (column-sum batch reduction, TMA refill, trig tables) -- see
 //             wigner_bwd_ws_kernel.  (per-sample spectrum, other C / degree ranges, ragged tails:
 //             wigner_bwd_kernel, where the tile lands by cp.async and the spectrum gradient
@@ -347,22 +347,25 @@ __device__ __forceinline__ void tma_load(void* smem_dst, const void* gsrc, uint3
 }
 
 // ------------------------------------------------------------------ backward, shared spectrum, warp-decoupled (sm_100a)
-// Same math as above, no group barriers.  One persistent 512-thread CTA per SM: 14 math warps and two producer warps,
+// Same math as above, no group barriers.  One persistent 512-thread CTA per SM: 11 math warps and five producer warps,
 // four (degrees 0..8) or six (0..6) 16-sample tile buffers in a ring (tile q of the CTA lives in buffer q % NB).
 //   * work item = (tile q, slice p): 32 of the tile's 160 (sample, channel) columns.  Math warps pull items in order from a
 //     shared-memory counter, so a warp that runs ahead (the scheduler favours high warp ids; SMSP 3 hosts one math warp
 //     less) simply takes more items -- nobody waits at a barrier for the slowest warp of a group.
 //   * a math warp waits for full[q % NB] (TMA bytes landed + trig table written), runs the backward chain on its 32
-//     columns (spectrum gradient in place, angle-gradient parts to gp), and arrives on empty[q % NB] (count 5).
-//   * the two producer warps (the last warps of the CTA: highest scheduling priority) own everything else.  For tile r,
-//     in ring order: wait empty -> column sums of the finished tile into 7 float2 registers per lane (this IS the batch
-//     reduction of the item_rep gradient: no atomics, no L2 reduce traffic, fixed order -> bit-reproducible) -> sum the
-//     angle-gradient parts over the 10 channels and store g_angles -> TMA bulk load of tile r + NB into the buffer (plus an
+//     columns (spectrum gradient in place, the column's generator forms T_x, T_y, T_z to gp), and arrives on empty[q % NB]
+//     (count 5).
+//   * the producer warps (the last warps of the CTA: highest scheduling priority) own everything else.  For tile r,
+//     in ring order: wait empty -> column sums of the finished tile into 3 float2 registers per lane (this IS the batch
+//     reduction of the item_rep gradient: no atomics, no L2 reduce traffic, fixed order -> bit-reproducible) -> TMA bulk load of tile r + NB into the buffer (plus an
 //     L2 prefetch of the tile after it) -> write the trig table of tile r + NB, which they computed *before* the wait
-//     from angles fetched one tile earlier still -> arrive on full.  The buffer's turnaround is column sums + one load
-//     latency; the other NB - 1 tiles are being computed or waiting meanwhile.
+//     from angles fetched one tile earlier still -> arrive on full; in the load's shadow: T_k summed over the 10 channels,
+//     the body-frame relation, g_angles stored.  The buffer's turnaround is column sums + one load latency; the other NB - 1
+//     tiles are being computed or waiting meanwhile.
 // Requires full 16-sample tiles and 16-byte aligned g_y (the host sends a ragged tail through wigner_bwd_kernel).
-// 14 math warps + 2 producer warps = 16 warps x 128 registers: the whole register file (warps are allocated in fours)
+// 11 math + 5 producer warps = 16 warps x 128 registers: the whole register file (warps are allocated in fours).  The split is
+// measured: since the angle gradients stopped needing the forward recompute the buffer turnaround (column sums + refill) binds,
+// and 13+3 / 12+4 / 11+5 / 10+6 / 9+7 warps run a 2^18-sample launch in 0.219 / 0.210 / 0.199 / 0.201 / 0.205 ms.
 #ifndef WD_MATH_WARPS_N
 #define WD_MATH_WARPS_N 11
 #endif
@@ -429,7 +432,7 @@ wigner_bwd_ws_kernel(const float* __restrict__ angles, const float* __restrict__
         }
     } else {
         // ------------------------------------------------------------ producer warps (pw = 0, 1)
-        const int pw = warp - WD_MATH_WARPS, pl = pw * 32 + lane;       // pl = 0..63: lane of the producer pair
+        const int pw = warp - WD_MATH_WARPS, pl = pw * 32 + lane;       // lane of the producer group
         f32x2_t acc[KACC];
 #pragma unroll
         for (int k = 0; k < KACC; ++k) acc[k] = 0ull;
