@@ -8,7 +8,8 @@ batch 1024, random-init weights -- one training step (forward, backward, Adam) w
   none    : the hot path replaced by a Linear stand-in (encoder + deconv only), to read off the hot path's share
 
 The conv encoder / deconv decoder are plain PyTorch with the reference's layer layout (experiments/nets.py:33-76,
-experiments/vae.py:56-120; degrees 6, rep_copies 10, group_reparam_in_dims 10, k = 10).  Measurement tooling, not product code.
+experiments/vae.py:56-120; degrees 6, rep_copies 10, group_reparam_in_dims 10, k = 10).  Measurement tooling that lives under tests/
+because its "before" arm executes the oracle (test infrastructure); not collected by pytest, not product code.
 """
 import argparse
 import json
