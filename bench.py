@@ -117,7 +117,7 @@ def cpu_reference_run(samples, steps, warmup, threads):
         y = O.action_net_forward(ang, it, L_MAX)
         loss = (y * gy).sum() + (lq * glq).sum()
         loss.backward()
-        return float(loss)
+        return float(loss.detach())
 
     for _ in range(warmup):
         step()

@@ -142,7 +142,7 @@ def run(hot, mean_mode, batch, steps, warm):
         loss = step()
     b.record()
     torch.cuda.synchronize()
-    return a.elapsed_time(b) / steps, float(loss)
+    return a.elapsed_time(b) / steps, float(loss.detach())
 
 
 def main():
