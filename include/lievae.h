@@ -143,6 +143,7 @@ int lv_so3_reparam_eazyz_bwd_f64(const double* mu, const double* sigma, const do
  *   mu    = mean_map(Wm h + bm)                mode 0: rodrigues (AlgebraMean reparameterize.py:148-155, Dm = 3)
  *                                              mode 1: quaternions_to_group_matrix (QuaternionMean :158-164, Dm = 4)
  *                                              mode 2: s2s2_gram_schmidt in float64 (S2S2Mean :184-197, Dm = 6)
+ *                                              mode 3: normalise, s2s1rodrigues (S2S1Mean :167-181, Dm = 5: rows [s2_map; s1_map])
  *   sigma = softplus(Ws h + bs)                (N0reparameterize reparameterize.py:117-121)
  *   then exactly lv_so3_reparam(_eazyz)_fwd.  Wm (Dm,Din), bm (Dm), Ws (3,Din), bs (3): the two Linear layers' parameters.
  *   mu (B,9) / sigma (B,3) are optional outputs (module attributes); give `angles` for the Euler-fused variant (z optional).

@@ -271,7 +271,7 @@ class SO3ReparamEazyz(Function):
         return sum_leading(gmu), sum_leading(gsg), None, None
 
 
-HEAD_MODES = {"alg": 0, "q": 1, "s2s2": 2}      # mean maps the fused head kernels know (rows of the mean head: 3, 4, 6)
+HEAD_MODES = {"alg": 0, "q": 1, "s2s2": 2, "s2s1": 3}      # mean maps the fused head kernels know (mean-head rows: 3, 4, 6, 5)
 HEAD_MAX_DIN = 32
 
 
@@ -290,7 +290,7 @@ class SO3HeadReparam(Function):
             if t.dtype != torch.float32:
                 raise TypeError("so3_head_reparameterize is float32 only, got %s" % t.dtype)
         m = HEAD_MODES[mode]
-        dm = (3, 4, 6)[m]
+        dm = (3, 4, 6, 5)[m]
         if h.dim() != 2 or h.shape[1] > HEAD_MAX_DIN:
             raise ValueError("h must be (B, Din <= %d), got %s" % (HEAD_MAX_DIN, tuple(h.shape)))
         B, Din = h.shape

@@ -1,9 +1,9 @@
 // Encoder heads fused into the SO(3) reparameterize kernels (sm_100a, FP32) -- SURVEY.md 8f-2.
 //
 // One kernel per direction replaces, for a batch of encoder features h (B, Din):
-//   mean head     Linear(Din -> 3 / 4 / 6)  + rodrigues / quaternions_to_group_matrix / s2s2_gram_schmidt
-//                 AlgebraMean reparameterize.py:148-155, QuaternionMean :158-164, S2S2Mean :184-197 (Gram-Schmidt in
-//                 float64 and cast back, exactly as :195-197)
+//   mean head     Linear(Din -> 3 / 4 / 5 / 6)  + rodrigues / quaternions_to_group_matrix / s2s1rodrigues / s2s2_gram_schmidt
+//                 AlgebraMean reparameterize.py:148-155, QuaternionMean :158-164, S2S1Mean :167-181 (axis and (cos, sin)
+//                 normalised first), S2S2Mean :184-197 (Gram-Schmidt in float64 and cast back, exactly as :195-197)
 //   sigma head    softplus(Linear(Din -> 3))                        N0reparameterize reparameterize.py:117-121
 //   sampling      v = eps * sigma, z = mu @ rodrigues(v), wrapped log-density, optionally matrix -> ZYZ Euler
 //                 (the body of reparam.cu, shared through reparam_core.cuh)
@@ -21,8 +21,8 @@
 namespace lv {
 
 constexpr int HR_TILE = 256, HR_WPAD = 12, HR_MAX_DIN = 32;
-enum { HR_ALG = 0, HR_QUAT = 1, HR_S2S2 = 2 };
-__host__ __device__ constexpr int hr_mean_rows(int mode) { return mode == HR_ALG ? 3 : mode == HR_QUAT ? 4 : 6; }
+enum { HR_ALG = 0, HR_QUAT = 1, HR_S2S2 = 2, HR_S2S1 = 3 };
+__host__ __device__ constexpr int hr_mean_rows(int mode) { return mode == HR_ALG ? 3 : mode == HR_QUAT ? 4 : mode == HR_S2S2 ? 6 : 5; }
 
 // softplus with torch's defaults (beta = 1, threshold = 20) and its derivative
 __device__ __forceinline__ float hr_softplus(float x) { return x > 20.f ? x : log1pf(expf(x)); }
@@ -32,7 +32,13 @@ template <int MODE>
 __device__ __forceinline__ void hr_mean_fwd(const float* pre, float (&m)[9]) {
     if (MODE == HR_ALG) rodrigues_fwd(pre, m);
     else if (MODE == HR_QUAT) quat_to_mat_fwd(pre, m);
-    else {
+    else if (MODE == HR_S2S1) {
+        // S2S1Mean (reparameterize.py:167-181): unit axis pre[0:3] / |.|, unit (cos, sin) pre[3:5] / |.|, then s2s1rodrigues
+        const float i2 = 1.f / sqrtf(pre[0] * pre[0] + pre[1] * pre[1] + pre[2] * pre[2]);
+        const float i1 = 1.f / sqrtf(pre[3] * pre[3] + pre[4] * pre[4]);
+        const float u[3] = {pre[0] * i2, pre[1] * i2, pre[2] * i2};
+        axis_angle_matrix(u, pre[4] * i1, 1.f - pre[3] * i1, m);
+    } else {
         double v1[3] = {pre[0], pre[1], pre[2]}, v2[3] = {pre[3], pre[4], pre[5]}, R[9];
         s2s2_fwd(v1, v2, R);
 #pragma unroll
@@ -43,7 +49,20 @@ template <int MODE>
 __device__ __forceinline__ void hr_mean_bwd(const float* pre, const float (&gm)[9], float* gpre) {
     if (MODE == HR_ALG) rodrigues_bwd(pre, gm, gpre);
     else if (MODE == HR_QUAT) quat_to_mat_bwd(pre, gm, gpre);
-    else {
+    else if (MODE == HR_S2S1) {
+        const float i2 = 1.f / sqrtf(pre[0] * pre[0] + pre[1] * pre[1] + pre[2] * pre[2]);
+        const float i1 = 1.f / sqrtf(pre[3] * pre[3] + pre[4] * pre[4]);
+        const float u[3] = {pre[0] * i2, pre[1] * i2, pre[2] * i2}, cs[2] = {pre[3] * i1, pre[4] * i1};
+        float gu[3], gs, gw;
+        axis_angle_matrix_bwd(u, cs[1], 1.f - cs[0], gm, gu, &gs, &gw);
+        const float gcs[2] = {-gw, gs};
+        // x -> x / |x|:  g_x = (g_e - e (e . g_e)) / |x|
+        const float du = u[0] * gu[0] + u[1] * gu[1] + u[2] * gu[2], dc = cs[0] * gcs[0] + cs[1] * gcs[1];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) gpre[j] = (gu[j] - u[j] * du) * i2;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) gpre[3 + j] = (gcs[j] - cs[j] * dc) * i1;
+    } else {
         double v1[3] = {pre[0], pre[1], pre[2]}, v2[3] = {pre[3], pre[4], pre[5]}, G[9], g1[3], g2[3];
 #pragma unroll
         for (int j = 0; j < 9; ++j) G[j] = gm[j];
@@ -250,7 +269,7 @@ head_reduce_partials(const float* __restrict__ partial, float* __restrict__ out,
 
 static int hr_check(const char* name, int64_t n, int64_t B, int Din, int mode, int k) {
     if (n < 0 || B < 0 || k < 0 || Din <= 0) { set_error("%s: bad sizes", name); return LV_ERR_ARG; }
-    if (mode < HR_ALG || mode > HR_S2S2) { set_error("%s: unknown mean mode %d", name, mode); return LV_ERR_ARG; }
+    if (mode < HR_ALG || mode > HR_S2S1) { set_error("%s: unknown mean mode %d", name, mode); return LV_ERR_ARG; }
     if (Din > HR_MAX_DIN) { set_error("%s: more than %d input features unsupported", name, HR_MAX_DIN); return LV_ERR_UNSUPPORTED; }
     if (k > 64) { set_error("%s: k=%d winding terms unsupported (max 64)", name, k); return LV_ERR_UNSUPPORTED; }
     if ((n * B + HR_TILE - 1) / HR_TILE > 0x7fffffffLL) { set_error("%s: too many samples", name); return LV_ERR_ARG; }
@@ -292,11 +311,12 @@ static int hr_launch_bwd(const float* h, const float* Wm, const float* bm, const
 #define HR_DISPATCH(mode, euler, FN, ...)                                                          \
     ((mode) == lv::HR_ALG ? ((euler) ? lv::FN<lv::HR_ALG, true>(__VA_ARGS__) : lv::FN<lv::HR_ALG, false>(__VA_ARGS__))       \
      : (mode) == lv::HR_QUAT ? ((euler) ? lv::FN<lv::HR_QUAT, true>(__VA_ARGS__) : lv::FN<lv::HR_QUAT, false>(__VA_ARGS__)) \
+     : (mode) == lv::HR_S2S1 ? ((euler) ? lv::FN<lv::HR_S2S1, true>(__VA_ARGS__) : lv::FN<lv::HR_S2S1, false>(__VA_ARGS__)) \
                              : ((euler) ? lv::FN<lv::HR_S2S2, true>(__VA_ARGS__) : lv::FN<lv::HR_S2S2, false>(__VA_ARGS__)))
 
 // ====================================================================== C ABI
 extern "C" int64_t lv_so3_head_reparam_bwd_workspace_floats(int64_t n, int64_t B, int Din, int mode) {
-    if (n < 0 || B < 0 || Din <= 0 || mode < lv::HR_ALG || mode > lv::HR_S2S2) return -1;
+    if (n < 0 || B < 0 || Din <= 0 || mode < lv::HR_ALG || mode > lv::HR_S2S1) return -1;
     return ((n * B + lv::HR_TILE - 1) / lv::HR_TILE) * int64_t(lv::hr_mean_rows(mode) + 3) * (Din + 1);
 }
 

@@ -148,7 +148,8 @@ def so3_head_reparameterize(h, mean_weight, mean_bias, sigma_weight, sigma_bias,
     """Encoder heads + reparameterize in ONE kernel.
 
     h (B,Din <= 32) encoder features; ``mean_weight`` (Dm,Din) / ``mean_bias`` (Dm) the mean head's Linear with
-    mode 'alg' (Dm = 3, ``AlgebraMean``), 'q' (Dm = 4, ``QuaternionMean``) or 's2s2' (Dm = 6, ``S2S2Mean``);
+    mode 'alg' (Dm = 3, ``AlgebraMean``), 'q' (Dm = 4, ``QuaternionMean``), 's2s2' (Dm = 6, ``S2S2Mean``) or 's2s1'
+    (Dm = 5, ``S2S1Mean``: rows of ``s2_map`` then ``s1_map``);
     ``sigma_weight`` (3,Din) / ``sigma_bias`` (3) the sigma head's; eps (n,B,3).
     Returns (z (n,B,3,3) -- or its ZYZ Euler angles (n,B,3) with ``euler`` --, log_q (n,B), mu (B,3,3), sigma (B,3)).
     Differentiable in h and the four head parameters.
@@ -290,17 +291,17 @@ class SO3reparameterize(nn.Module):
         self.mu_lie, self.v, self.z = None, None, None
         self._log_q = None
         # encoder heads (Linear + mean map, Linear + softplus) inside the reparameterize kernel when the mean module
-        # is AlgebraMean / QuaternionMean / S2S2Mean on float32 CUDA features; set False for the unfused launches
+        # is one of the four reference mean maps on float32 CUDA features; set False for the unfused launches
         self.fuse_heads = True
         self._fused_input = None
 
     def _fused_head_mode(self, x):
         """'alg' / 'q' / 's2s2' when the encoder heads can run inside the reparameterize kernel, else None."""
-        mode = {AlgebraMean: "alg", QuaternionMean: "q", S2S2Mean: "s2s2"}.get(type(self.mean_module))
+        mode = {AlgebraMean: "alg", QuaternionMean: "q", S2S2Mean: "s2s2", S2S1Mean: "s2s1"}.get(type(self.mean_module))
         rep = self.reparameterize
         ok = (self.fuse_heads and mode is not None and type(rep) is N0reparameterize and rep.fixed_sigma is None
               and not self.return_means and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2
-              and x.shape[1] <= _ops.HEAD_MAX_DIN and self.mean_module.map.weight.dtype == torch.float32)
+              and x.shape[1] <= _ops.HEAD_MAX_DIN and rep.sigma_linear.weight.dtype == torch.float32)
         return mode if ok else None
 
     def _forward_fused(self, x, n, mode):
@@ -310,8 +311,12 @@ class SO3reparameterize(nn.Module):
             rep.eps = rep.sample_noise(n, like=x)
         except TypeError:                                   # a user-supplied sample_noise(n) without the keyword
             rep.eps = rep.sample_noise(n)
+        if mode == "s2s1":      # two Linear layers feed this mean map: stack them (axis rows, then (cos, sin) rows)
+            wm, bm = torch.cat([mean.s2_map.weight, mean.s1_map.weight], 0), torch.cat([mean.s2_map.bias, mean.s1_map.bias], 0)
+        else:
+            wm, bm = mean.map.weight, mean.map.bias
         self.z, self._log_q, self.mu_lie, rep.sigma = _ops.SO3HeadReparam.apply(
-            x, mean.map.weight, mean.map.bias, rep.sigma_linear.weight, rep.sigma_linear.bias, rep.eps, mode, self.k, False)
+            x, wm, bm, rep.sigma_linear.weight, rep.sigma_linear.bias, rep.eps, mode, self.k, False)
         self._fused_input = (x, mode)                       # nsample() re-runs the heads so that gradients keep flowing
         self.v = rep.eps * rep.sigma
         rep.z = self.v

@@ -459,14 +459,15 @@ def test_wigner_backward_accumulate_flag(mods, L, C, N):
 
 # ----------------------------------------------------------------------- encoder heads fused into the reparameterize kernel
 @pytest.mark.parametrize("mode,n,B,Din,k", [("alg", 1, 1000, 10, 10), ("q", 3, 777, 10, 3), ("s2s2", 1, 513, 10, 10),
-                                            ("alg", 2, 64, 32, 5), ("q", 1, 5, 7, 0), ("s2s2", 2, 300, 16, 3)])
+                                            ("alg", 2, 64, 32, 5), ("q", 1, 5, 7, 0), ("s2s2", 2, 300, 16, 3),
+                                            ("s2s1", 1, 900, 10, 10), ("s2s1", 3, 77, 20, 3)])
 def test_fused_heads_match_unfused_modules(mods, mode, n, B, Din, k):
     """SO3reparameterize with the heads inside the kernel (the default) against the same module with fuse_heads = False
     (Linear -> mean map kernel -> softplus -> reparameterize kernel): z, log_q, mu_lie, sigma, kl and the gradients of the
     features and of every head parameter."""
     _, rp, _ = mods
     torch.manual_seed(B + Din)
-    mean_cls = {"alg": rp.AlgebraMean, "q": rp.QuaternionMean, "s2s2": rp.S2S2Mean}[mode]
+    mean_cls = {"alg": rp.AlgebraMean, "q": rp.QuaternionMean, "s2s2": rp.S2S2Mean, "s2s1": rp.S2S1Mean}[mode]
     mod = rp.SO3reparameterize(rp.N0reparameterize(Din, 3), mean_cls(Din), k=k).cuda()
     if mode == "s2s2":
         mod.mean_module.map.weight.data.uniform_(-1, 1)
@@ -536,9 +537,8 @@ def test_fused_heads_nsample_and_fallbacks(mods):
     assert tuple(z.shape) == (4, 40, 3, 3)
     z.sum().backward()
     assert x.grad is not None and x.grad.abs().sum().item() > 0 and mod.mean_module.map.weight.grad is not None
-    # paths the fused kernel does not cover fall back to the separate launches: S2S1 mean, fixed sigma, wide features, float64
-    for m2, xin in ((rp.SO3reparameterize(rp.N0reparameterize(10, 3), rp.S2S1Mean(10)).cuda(), torch.randn(8, 10, device="cuda")),
-                    (rp.SO3reparameterize(rp.N0reparameterize(10, 3, fixed_sigma=0.3), rp.AlgebraMean(10)).cuda(), torch.randn(8, 10, device="cuda")),
+    # paths the fused kernel does not cover fall back to the separate launches: fixed sigma, wide features, float64
+    for m2, xin in ((rp.SO3reparameterize(rp.N0reparameterize(10, 3, fixed_sigma=0.3), rp.AlgebraMean(10)).cuda(), torch.randn(8, 10, device="cuda")),
                     (rp.SO3reparameterize(rp.N0reparameterize(40, 3), rp.AlgebraMean(40)).cuda(), torch.randn(8, 40, device="cuda")),
                     (rp.SO3reparameterize(rp.N0reparameterize(10, 3), rp.QuaternionMean(10)).cuda().double(), torch.randn(8, 10, device="cuda", dtype=torch.float64))):
         out = m2(xin)
