@@ -31,6 +31,8 @@ template <> struct Sc<float> {
     static __device__ __forceinline__ float abs(float x) { return fabsf(x); }
     static __device__ __forceinline__ float fma(float a, float b, float c) { return fmaf(a, b, c); }
     static __device__ __forceinline__ float max(float a, float b) { return fmaxf(a, b); }
+    static __device__ __forceinline__ float min(float a, float b) { return fminf(a, b); }
+    static __device__ __forceinline__ float rint(float x) { return rintf(x); }
     static __device__ __forceinline__ float log(float x) { return logf(x); }
     static __device__ __forceinline__ float exp(float x) { return expf(x); }
 };
@@ -44,6 +46,8 @@ template <> struct Sc<double> {
     static __device__ __forceinline__ double abs(double x) { return ::fabs(x); }
     static __device__ __forceinline__ double fma(double a, double b, double c) { return ::fma(a, b, c); }
     static __device__ __forceinline__ double max(double a, double b) { return ::fmax(a, b); }
+    static __device__ __forceinline__ double min(double a, double b) { return ::fmin(a, b); }
+    static __device__ __forceinline__ double rint(double x) { return ::rint(x); }
     static __device__ __forceinline__ double log(double x) { return ::log(x); }
     static __device__ __forceinline__ double exp(double x) { return ::exp(x); }
 };

@@ -10,103 +10,93 @@ constexpr double RP_CLAMP = 1e-3;
 constexpr double RP_TWO_PI = 6.283185307179586476925;
 constexpr double RP_LOG_2PI_1P5 = 2.756815599614018102;   // 1.5 * log(2 pi)
 
-// per-term log / exp / divide: fast intrinsics in float (one MUFU each; the final log of the LSE is full precision),
-// the library functions in double
-__device__ __forceinline__ float rp_log(float x) { return __logf(x); }
-__device__ __forceinline__ float rp_exp(float x) { return __expf(x); }
-__device__ __forceinline__ float rp_div(float a, float b) { return __fdividef(a, b); }
-__device__ __forceinline__ double rp_log(double x) { return ::log(x); }
-__device__ __forceinline__ double rp_exp(double x) { return ::exp(x); }
-__device__ __forceinline__ double rp_div(double a, double b) { return a / b; }
-template <typename T> __device__ __forceinline__ T rp_neg_inf();
-template <> __device__ __forceinline__ float rp_neg_inf<float>() { return -INFINITY; }
-template <> __device__ __forceinline__ double rp_neg_inf<double>() { return -HUGE_VAL; }
+// per-term exponential: float uses the MUFU base-2 exponential directly (the caller pre-scales the exponent by log2 e, so a
+// winding costs FADD + FMUL + MUFU.EX2 + FFMA); double uses the library exp (scale 1).  The final log of the sum is full
+// precision in both.
+template <typename T> constexpr double RP_EXP_SCALE = 1.0;
+template <> constexpr double RP_EXP_SCALE<float> = 1.442695040888963407;   // log2(e)
+__device__ __forceinline__ float rp_exp2s(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ double rp_exp2s(double x) { return ::exp(x); }
+// theta + 2 pi k with the product rounded separately (never contracted into an FMA): the reference point of the sum and
+// the matching term of the loop are then bit-identical, so that term's exponent is exactly 0 -- and it is the rounding the
+// reference's own tensor expression theta + 2 pi k performs (reparameterize.py:246-247).
+__device__ __forceinline__ float winding_theta(float theta, float k) { return theta + __fmul_rn(float(RP_TWO_PI), k); }
+__device__ __forceinline__ double winding_theta(double theta, double k) { return theta + __dmul_rn(RP_TWO_PI, k); }
 
 // ------------------------------------------------------------------ wrapped log-density terms
-// KT > 0: winding count known at compile time (terms live in registers, one pass of logs);
-// KT == 0: runtime K, two passes (max, then sum) recomputing the terms.
-template <typename T, int KT>
-__device__ __forceinline__ T winding_lse(T theta, T a, int krt) {
-    if constexpr (KT > 0) {
-        T t[2 * KT + 1];
-        T m = rp_neg_inf<T>();
-#pragma unroll
-        for (int i = 0; i < 2 * KT + 1; ++i) {
-            const T th = theta + T(RP_TWO_PI) * T(i - KT);
-            const T x = th * th;
-            t[i] = Sc<T>::fma(-a, x, rp_log(Sc<T>::max(x, T(RP_CLAMP))));
-            m = Sc<T>::max(m, t[i]);
-        }
-        T s = T(0);
-#pragma unroll
-        for (int i = 0; i < 2 * KT + 1; ++i) s += rp_exp(t[i] - m);
-        return m + Sc<T>::log(s);
-    } else {
-        T m = rp_neg_inf<T>();
-        for (int k = -krt; k <= krt; ++k) {
-            const T th = theta + T(RP_TWO_PI) * T(k);
-            const T x = th * th;
-            m = Sc<T>::max(m, Sc<T>::fma(-a, x, rp_log(Sc<T>::max(x, T(RP_CLAMP)))));
-        }
-        T s = T(0);
-        for (int k = -krt; k <= krt; ++k) {
-            const T th = theta + T(RP_TWO_PI) * T(k);
-            const T x = th * th;
-            s += rp_exp(Sc<T>::fma(-a, x, rp_log(Sc<T>::max(x, T(RP_CLAMP)))) - m);
-        }
-        return m + Sc<T>::log(s);
-    }
+// Term k of the winding sum is  t_k = -a x_k + log max(x_k, c),  x_k = (theta + 2 pi k)^2  (reparameterize.py:246-259), so
+//   exp(t_k - ref) = max(x_k, c) * E_k,   E_k = exp(-a (x_k - x_ref)),
+// and neither the per-term log nor (in the backward) the per-term 2/th_k divide is needed: one exponential per
+// winding (the exponent is formed from the difference x_k - x_ref, so its rounding error is relative to the exponent, not to
+// a x_k as in a per-term evaluation).  x_ref = x of the winding nearest to zero among k = -K..K (every exponent <= 0, the nearest term has E = 1, and
+// the sum stays within [c, (2K+1) (theta + 2 pi K)^2]: no overflow or underflow).  LSE = -a x_ref + log(sum).
+// KT > 0: winding count known at compile time (fully unrolled); KT == 0: runtime K.
+template <typename T>
+__device__ __forceinline__ T winding_ref(T theta, int K) {
+    // nearest allowed winding: k* = clamp(round(-theta / 2 pi), -K, K)
+    T ks = Sc<T>::rint(-theta * T(1.0 / RP_TWO_PI));
+    ks = Sc<T>::max(T(-K), Sc<T>::min(T(K), ks));
+    const T th = winding_theta(theta, ks);
+    return th * th;
 }
 
-// softmax-weighted sums needed by the backward:
-//   d1 = sum_k w_k (-2 a th_k + [th_k^2 >= c] 2/th_k)    (d LSE / d theta)
-//   e2 = sum_k w_k th_k^2                                 (-d LSE / d a)
 template <typename T, int KT>
-__device__ __forceinline__ void winding_grad(T theta, T a, int krt, T* d1, T* e2) {
-    T m = rp_neg_inf<T>();
+__device__ __forceinline__ T winding_lse(T theta, T a, int krt) {
+    const int K = KT > 0 ? KT : krt;
+    const T xr = winding_ref(theta, K);
+    const T a2 = -a * T(RP_EXP_SCALE<T>);         // exponent in the base rp_exp2s works in
+    T s = T(0);
     if constexpr (KT > 0) {
-        T t[2 * KT + 1];
 #pragma unroll
         for (int i = 0; i < 2 * KT + 1; ++i) {
-            const T th = theta + T(RP_TWO_PI) * T(i - KT);
+            const T th = winding_theta(theta, T(i - KT));
             const T x = th * th;
-            t[i] = Sc<T>::fma(-a, x, rp_log(Sc<T>::max(x, T(RP_CLAMP))));
-            m = Sc<T>::max(m, t[i]);
+            s = Sc<T>::fma(Sc<T>::max(x, T(RP_CLAMP)), rp_exp2s(a2 * (x - xr)), s);
         }
-        T s = T(0), s1 = T(0), s2 = T(0);
-#pragma unroll
-        for (int i = 0; i < 2 * KT + 1; ++i) {
-            const T th = theta + T(RP_TWO_PI) * T(i - KT);
-            const T x = th * th;
-            const T e = rp_exp(t[i] - m);
-            const T dl = x >= T(RP_CLAMP) ? rp_div(T(2), th) : T(0);
-            s += e;
-            s1 = Sc<T>::fma(e, Sc<T>::fma(T(-2) * a, th, dl), s1);
-            s2 = Sc<T>::fma(e, x, s2);
-        }
-        const T inv = T(1) / s;
-        *d1 = s1 * inv;
-        *e2 = s2 * inv;
     } else {
         for (int k = -krt; k <= krt; ++k) {
-            const T th = theta + T(RP_TWO_PI) * T(k);
+            const T th = winding_theta(theta, T(k));
             const T x = th * th;
-            m = Sc<T>::max(m, Sc<T>::fma(-a, x, rp_log(Sc<T>::max(x, T(RP_CLAMP)))));
+            s = Sc<T>::fma(Sc<T>::max(x, T(RP_CLAMP)), rp_exp2s(a2 * (x - xr)), s);
         }
-        T s = T(0), s1 = T(0), s2 = T(0);
-        for (int k = -krt; k <= krt; ++k) {
-            const T th = theta + T(RP_TWO_PI) * T(k);
-            const T x = th * th;
-            const T e = rp_exp(Sc<T>::fma(-a, x, rp_log(Sc<T>::max(x, T(RP_CLAMP)))) - m);
-            const T dl = x >= T(RP_CLAMP) ? rp_div(T(2), th) : T(0);
-            s += e;
-            s1 = Sc<T>::fma(e, Sc<T>::fma(T(-2) * a, th, dl), s1);
-            s2 = Sc<T>::fma(e, x, s2);
-        }
-        const T inv = T(1) / s;
-        *d1 = s1 * inv;
-        *e2 = s2 * inv;
     }
+    return Sc<T>::fma(-a, xr, Sc<T>::log(s));
+}
+
+// softmax-weighted sums needed by the backward, w_k = max(x_k, c) E_k / sum:
+//   d1 = sum_k w_k (-2 a th_k + [x_k >= c] 2/th_k) = sum_k E_k th_k ([x_k >= c] 2 - 2 a max(x_k, c)) / sum   (d LSE / d theta)
+//   e2 = sum_k w_k x_k                                                                                         (-d LSE / d a)
+template <typename T>
+__device__ __forceinline__ void winding_grad_term(T th, T a, T a2, T xr, T& s, T& s1, T& s2) {
+    const T x = th * th;
+    const T e = rp_exp2s(a2 * (x - xr));
+    const T xc = Sc<T>::max(x, T(RP_CLAMP));
+    const T w = xc * e;
+    const T dl = x >= T(RP_CLAMP) ? T(2) : T(0);
+    s += w;
+    s1 = Sc<T>::fma(e * th, Sc<T>::fma(T(-2) * a, xc, dl), s1);
+    s2 = Sc<T>::fma(w, x, s2);
+}
+
+template <typename T, int KT>
+__device__ __forceinline__ void winding_grad(T theta, T a, int krt, T* d1, T* e2) {
+    const int K = KT > 0 ? KT : krt;
+    const T xr = winding_ref(theta, K);
+    const T a2 = -a * T(RP_EXP_SCALE<T>);
+    T s = T(0), s1 = T(0), s2 = T(0);
+    if constexpr (KT > 0) {
+#pragma unroll
+        for (int i = 0; i < 2 * KT + 1; ++i) winding_grad_term(winding_theta(theta, T(i - KT)), a, a2, xr, s, s1, s2);
+    } else {
+        for (int k = -krt; k <= krt; ++k) winding_grad_term(winding_theta(theta, T(k)), a, a2, xr, s, s1, s2);
+    }
+    const T inv = T(1) / s;
+    *d1 = s1 * inv;
+    *e2 = s2 * inv;
 }
 
 // ------------------------------------------------------------------ one sample, forward
