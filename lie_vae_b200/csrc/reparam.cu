@@ -16,9 +16,14 @@
 //
 // Layout: mu (B,3,3) = 9-float rows, sigma (B,3), eps (n,B,3), z (n,B,3,3), log_q (n,B);
 // the sample index is flat over (n,B), mu/sigma broadcast over n (b = i mod B).  One thread
-// per sample; each CTA stages its 256-sample tile through shared memory with 128-bit
-// coalesced accesses (rows of 9 and 3 floats are odd strides -> conflict-free LDS), all
-// arithmetic in registers, outputs written back through the same staging buffers.
+// per sample; each CTA stages its 256-sample tile through shared memory (rows of 9 and 3
+// floats are odd strides -> conflict-free LDS), all arithmetic in registers, outputs written
+// back through the same staging buffers.  A tile is one contiguous span of every tensor, so
+// full tiles move with TMA bulk copies issued by ONE thread (cp.async.bulk + mbarrier in,
+// cp.async.bulk.global.shared::cta out): the kernels are issue-bound and the per-thread
+// cp.async / store loops (addresses, alignment and bound checks: ~120 + ~60 of the ~800
+// instructions a thread executed) are what this removes.  Ragged last tiles, tiles that wrap
+// over the broadcast rows and unaligned tensors take the cp.async path.
 // HBM-bound: 100 B/sample forward, 148 B/sample backward.
 #include "common.cuh"
 #include "reparam_core.cuh"
@@ -43,6 +48,14 @@ __device__ __forceinline__ void stage_bcast(T* __restrict__ dst, const T* __rest
     }
 }
 
+// A full tile can move with TMA bulk copies when every tensor is 16-byte aligned (host flag), the tile does not wrap
+// over the broadcast mu / sigma rows, and its first broadcast row starts on a 16-byte boundary (rows are 36 / 12 bytes
+// in float, 72 / 24 in double: b0 a multiple of 4 covers all of them; the tile's own start i0 is a multiple of TILE).
+template <int TILE>
+__device__ __forceinline__ bool bulk_tile_ok(int aligned16, bool full, int64_t b0, int64_t B) {
+    return aligned16 != 0 && full && b0 + TILE <= B && (b0 & 3) == 0;
+}
+
 // ------------------------------------------------------------------ forward
 // EULER: additionally emit the ZYZ Euler angles of z (group_matrix_to_eazyz, lie_tools.py:178-180 -- what
 // VAE.decode feeds the action decoder, vae.py:182) from the registers that hold z; z itself is then optional.
@@ -50,19 +63,35 @@ template <typename T, int KT, bool EULER, int TILE>
 __global__ void __launch_bounds__(TILE)
 so3_reparam_fwd_kernel(const T* __restrict__ mu, const T* __restrict__ sigma, const T* __restrict__ eps,
                        T* __restrict__ z, T* __restrict__ angles, T* __restrict__ log_q, int64_t total,
-                       int64_t B, int krt) {
+                       int64_t B, int krt, int aligned16) {
     __shared__ __align__(16) T s_m[TILE * 9];   // mu in, z out (same row, same thread)
     __shared__ __align__(16) T s_s[TILE * 3];
     __shared__ __align__(16) T s_e[TILE * 3];   // eps in, Euler angles out
+    __shared__ __align__(8) uint64_t s_bar;
     const int64_t i0 = int64_t(blockIdx.x) * TILE;
     const int rows = int(min(int64_t(TILE), total - i0));
-    stage_bcast<T, 9, TILE>(s_m, mu, i0, rows, B);
-    stage_bcast<T, 3, TILE>(s_s, sigma, i0, rows, B);
     const bool full = rows == TILE;       // every CTA but the last: compile-time copy loops
-    if (full) tile_g2s_full<T, TILE * 3, TILE>(s_e, eps + i0 * 3);
-    else tile_g2s(s_e, eps + i0 * 3, rows * 3);
-    tile_async_wait();
-    __syncthreads();
+    const int64_t b0 = i0 < B ? i0 : i0 % B;
+    const bool bulk = bulk_tile_ok<TILE>(aligned16, full, b0, B);
+    if (bulk) {
+        if (threadIdx.x == 0) {
+            mbar_init(&s_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_expect_tx(&s_bar, uint32_t(TILE * 15 * sizeof(T)));
+            tma_load(s_m, mu + b0 * 9, uint32_t(TILE * 9 * sizeof(T)), &s_bar);
+            tma_load(s_s, sigma + b0 * 3, uint32_t(TILE * 3 * sizeof(T)), &s_bar);
+            tma_load(s_e, eps + i0 * 3, uint32_t(TILE * 3 * sizeof(T)), &s_bar);
+        }
+        __syncthreads();                  // the barrier word is initialised before anyone polls it
+        mbar_wait(&s_bar, 0);
+    } else {
+        stage_bcast<T, 9, TILE>(s_m, mu, i0, rows, B);
+        stage_bcast<T, 3, TILE>(s_s, sigma, i0, rows, B);
+        if (full) tile_g2s_full<T, TILE * 3, TILE>(s_e, eps + i0 * 3);
+        else tile_g2s(s_e, eps + i0 * 3, rows * 3);
+        tile_async_wait();
+        __syncthreads();
+    }
     const int t = threadIdx.x;
     if (t < rows) {
         T m[9], sg[3], ep[3], zr[9], e[3], lq;
@@ -78,6 +107,16 @@ so3_reparam_fwd_kernel(const T* __restrict__ mu, const T* __restrict__ sigma, co
             for (int j = 0; j < 3; ++j) s_e[t * 3 + j] = e[j];
         }
         if (log_q != nullptr) log_q[i0 + t] = lq;
+    }
+    if (bulk) {
+        fence_proxy_async_smem();         // this thread's smem writes -> visible to the copy engine
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (z != nullptr) tma_store(z + i0 * 9, s_m, uint32_t(TILE * 9 * sizeof(T)));
+            if (EULER) tma_store(angles + i0 * 3, s_e, uint32_t(TILE * 3 * sizeof(T)));
+            tma_store_commit_wait();
+        }
+        return;
     }
     __syncthreads();
     if (full) {
@@ -97,28 +136,46 @@ template <typename T, int KT, bool EULER, int TILE>
 __global__ void __launch_bounds__(TILE)
 so3_reparam_bwd_kernel(const T* __restrict__ mu, const T* __restrict__ sigma, const T* __restrict__ eps,
                        const T* __restrict__ gz, const T* __restrict__ gangles, const T* __restrict__ glq,
-                       T* __restrict__ gmu, T* __restrict__ gsigma, int64_t total, int64_t B, int krt) {
+                       T* __restrict__ gmu, T* __restrict__ gsigma, int64_t total, int64_t B, int krt, int aligned16) {
     __shared__ __align__(16) T s_m[TILE * 9];
     __shared__ __align__(16) T s_g[TILE * 9];   // gz in, g_mu out
     __shared__ __align__(16) T s_s[TILE * 3];
     __shared__ __align__(16) T s_e[TILE * 3];   // eps in, g_sigma out
     __shared__ __align__(16) T s_a[EULER ? TILE * 3 : 4];   // g_angles in
+    __shared__ __align__(8) uint64_t s_bar;
     const int64_t i0 = int64_t(blockIdx.x) * TILE;
     const int rows = int(min(int64_t(TILE), total - i0));
-    stage_bcast<T, 9, TILE>(s_m, mu, i0, rows, B);
-    stage_bcast<T, 3, TILE>(s_s, sigma, i0, rows, B);
     const bool full = rows == TILE;
-    if (full) {
-        tile_g2s_full<T, TILE * 3, TILE>(s_e, eps + i0 * 3);
-        if (gz != nullptr) tile_g2s_full<T, TILE * 9, TILE>(s_g, gz + i0 * 9);
-        if (EULER) tile_g2s_full<T, TILE * 3, TILE>(s_a, gangles + i0 * 3);
+    const int64_t b0 = i0 < B ? i0 : i0 % B;
+    const bool bulk = bulk_tile_ok<TILE>(aligned16, full, b0, B);
+    if (bulk) {
+        if (threadIdx.x == 0) {
+            mbar_init(&s_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_expect_tx(&s_bar, uint32_t(TILE * (15 + (gz != nullptr ? 9 : 0) + (EULER ? 3 : 0)) * sizeof(T)));
+            tma_load(s_m, mu + b0 * 9, uint32_t(TILE * 9 * sizeof(T)), &s_bar);
+            tma_load(s_s, sigma + b0 * 3, uint32_t(TILE * 3 * sizeof(T)), &s_bar);
+            tma_load(s_e, eps + i0 * 3, uint32_t(TILE * 3 * sizeof(T)), &s_bar);
+            if (gz != nullptr) tma_load(s_g, gz + i0 * 9, uint32_t(TILE * 9 * sizeof(T)), &s_bar);
+            if (EULER) tma_load(s_a, gangles + i0 * 3, uint32_t(TILE * 3 * sizeof(T)), &s_bar);
+        }
+        __syncthreads();
+        mbar_wait(&s_bar, 0);
     } else {
-        tile_g2s(s_e, eps + i0 * 3, rows * 3);
-        if (gz != nullptr) tile_g2s(s_g, gz + i0 * 9, rows * 9);
-        if (EULER) tile_g2s(s_a, gangles + i0 * 3, rows * 3);
+        stage_bcast<T, 9, TILE>(s_m, mu, i0, rows, B);
+        stage_bcast<T, 3, TILE>(s_s, sigma, i0, rows, B);
+        if (full) {
+            tile_g2s_full<T, TILE * 3, TILE>(s_e, eps + i0 * 3);
+            if (gz != nullptr) tile_g2s_full<T, TILE * 9, TILE>(s_g, gz + i0 * 9);
+            if (EULER) tile_g2s_full<T, TILE * 3, TILE>(s_a, gangles + i0 * 3);
+        } else {
+            tile_g2s(s_e, eps + i0 * 3, rows * 3);
+            if (gz != nullptr) tile_g2s(s_g, gz + i0 * 9, rows * 9);
+            if (EULER) tile_g2s(s_a, gangles + i0 * 3, rows * 3);
+        }
+        tile_async_wait();
+        __syncthreads();
     }
-    tile_async_wait();
-    __syncthreads();
     const int t = threadIdx.x;
     if (t < rows) {
         T m[9], G[9], sg[3], ep[3], ge[3] = {T(0), T(0), T(0)}, gm[9], gsg[3];
@@ -136,6 +193,16 @@ so3_reparam_bwd_kernel(const T* __restrict__ mu, const T* __restrict__ sigma, co
         for (int j = 0; j < 9; ++j) s_g[t * 9 + j] = gm[j];
 #pragma unroll
         for (int j = 0; j < 3; ++j) s_e[t * 3 + j] = gsg[j];
+    }
+    if (bulk) {
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            tma_store(gmu + i0 * 9, s_g, uint32_t(TILE * 9 * sizeof(T)));
+            tma_store(gsigma + i0 * 3, s_e, uint32_t(TILE * 3 * sizeof(T)));
+            tma_store_commit_wait();
+        }
+        return;
     }
     __syncthreads();
     if (full) {
@@ -157,6 +224,11 @@ static int reparam_check(const char* name, int64_t n, int64_t B, int k) {
     return LV_OK;
 }
 
+template <typename... P>
+static int aligned16(const P*... p) {
+    return (((reinterpret_cast<uintptr_t>(p)) | ...) & 15u) == 0;
+}
+
 template <typename T, bool EULER>
 static int reparam_fwd(const char* name, const T* mu, const T* sigma, const T* eps, T* z, T* angles,
                        T* log_q, int64_t n, int64_t B, int k, void* stream) {
@@ -168,10 +240,11 @@ static int reparam_fwd(const char* name, const T* mu, const T* sigma, const T* e
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     constexpr int TILE = sizeof(T) == 8 ? lv::RP_TILE / 2 : lv::RP_TILE;
     const unsigned grid = unsigned((total + TILE - 1) / TILE);
-    if constexpr (sizeof(T) == 8) lv::so3_reparam_fwd_kernel<T, 0, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, z, angles, log_q, total, B, k);
-    else if (k == 3) lv::so3_reparam_fwd_kernel<T, 3, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, z, angles, log_q, total, B, k);
-    else if (k == 10) lv::so3_reparam_fwd_kernel<T, 10, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, z, angles, log_q, total, B, k);
-    else lv::so3_reparam_fwd_kernel<T, 0, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, z, angles, log_q, total, B, k);
+    const int al = aligned16(mu, sigma, eps, z, angles);      // null pointers count as aligned
+    if constexpr (sizeof(T) == 8) lv::so3_reparam_fwd_kernel<T, 0, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, z, angles, log_q, total, B, k, al);
+    else if (k == 3) lv::so3_reparam_fwd_kernel<T, 3, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, z, angles, log_q, total, B, k, al);
+    else if (k == 10) lv::so3_reparam_fwd_kernel<T, 10, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, z, angles, log_q, total, B, k, al);
+    else lv::so3_reparam_fwd_kernel<T, 0, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, z, angles, log_q, total, B, k, al);
     return lv::check_launch(name);
 }
 
@@ -187,10 +260,11 @@ static int reparam_bwd(const char* name, const T* mu, const T* sigma, const T* e
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     constexpr int TILE = sizeof(T) == 8 ? lv::RP_TILE / 2 : lv::RP_TILE;
     const unsigned grid = unsigned((total + TILE - 1) / TILE);
-    if constexpr (sizeof(T) == 8) lv::so3_reparam_bwd_kernel<T, 0, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, total, B, k);
-    else if (k == 3) lv::so3_reparam_bwd_kernel<T, 3, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, total, B, k);
-    else if (k == 10) lv::so3_reparam_bwd_kernel<T, 10, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, total, B, k);
-    else lv::so3_reparam_bwd_kernel<T, 0, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, total, B, k);
+    const int al = aligned16(mu, sigma, eps, gz, gangles, gmu, gsigma);
+    if constexpr (sizeof(T) == 8) lv::so3_reparam_bwd_kernel<T, 0, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, total, B, k, al);
+    else if (k == 3) lv::so3_reparam_bwd_kernel<T, 3, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, total, B, k, al);
+    else if (k == 10) lv::so3_reparam_bwd_kernel<T, 10, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, total, B, k, al);
+    else lv::so3_reparam_bwd_kernel<T, 0, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, total, B, k, al);
     return lv::check_launch(name);
 }
 

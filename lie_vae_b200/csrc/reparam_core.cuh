@@ -44,10 +44,12 @@ __device__ __forceinline__ T winding_ref(T theta, int K) {
     return th * th;
 }
 
+// returns sum_k max(x_k, c) E_k and the reference x_ref:  LSE_k t_k = -a x_ref + log(sum)
 template <typename T, int KT>
-__device__ __forceinline__ T winding_lse(T theta, T a, int krt) {
+__device__ __forceinline__ T winding_sum(T theta, T a, int krt, T* xref) {
     const int K = KT > 0 ? KT : krt;
     const T xr = winding_ref(theta, K);
+    *xref = xr;
     const T a2 = -a * T(RP_EXP_SCALE<T>);         // exponent in the base rp_exp2s works in
     T s = T(0);
     if constexpr (KT > 0) {
@@ -64,7 +66,15 @@ __device__ __forceinline__ T winding_lse(T theta, T a, int krt) {
             s = Sc<T>::fma(Sc<T>::max(x, T(RP_CLAMP)), rp_exp2s(a2 * (x - xr)), s);
         }
     }
-    return Sc<T>::fma(-a, xr, Sc<T>::log(s));
+    return s;
+}
+
+// log(s0 s1 s2): one log of the product while no partial product can leave the normal range, else the three logs
+template <typename T>
+__device__ __forceinline__ T log_prod3(const T (&sg)[3]) {
+    const T lo = Sc<T>::min(sg[0], Sc<T>::min(sg[1], sg[2])), hi = Sc<T>::max(sg[0], Sc<T>::max(sg[1], sg[2]));
+    if (lo > T(1e-12) && hi < T(1e12)) return Sc<T>::log(sg[0] * sg[1] * sg[2]);
+    return Sc<T>::log(sg[0]) + Sc<T>::log(sg[1]) + Sc<T>::log(sg[2]);
 }
 
 // softmax-weighted sums needed by the backward, w_k = max(x_k, c) E_k / sum:
@@ -123,9 +133,12 @@ __device__ __forceinline__ void reparam_sample_fwd(const T (&m)[9], const T (&sg
     if (want_lq) {
         const T q0 = k.u[0] / sg[0], q1 = k.u[1] / sg[1], q2 = k.u[2] / sg[2];
         const T a = T(0.5) * (q0 * q0 + q1 * q1 + q2 * q2);
-        const T lse = winding_lse<T, KT>(k.theta, a, krt);
+        // log_q = LSE - sum_i log sigma_i - 1.5 log 2 pi - log den with LSE = -a x_ref + log(sum): two logs instead of five
+        // (sum in [c, (2K+1) max x] and den in [c, 4]: the quotient stays far inside the normal range)
+        T xr;
+        const T sum = winding_sum<T, KT>(k.theta, a, krt, &xr);
         const T den = Sc<T>::max(T(2) * k.w, T(RP_CLAMP));
-        *lq = lse - (Sc<T>::log(sg[0]) + Sc<T>::log(sg[1]) + Sc<T>::log(sg[2])) - T(RP_LOG_2PI_1P5) - Sc<T>::log(den);
+        *lq = Sc<T>::fma(-a, xr, Sc<T>::log(sum / den)) - log_prod3(sg) - T(RP_LOG_2PI_1P5);
     }
 }
 

@@ -101,6 +101,46 @@ def test_reparam_large_vs_oracle(mods, k):
     as_good_as_ref32(sgg.grad, gsg64, gsg32, "g_sigma")
 
 
+@pytest.mark.parametrize("k", [0, 1, 3, 10])
+@pytest.mark.parametrize("regime", ["narrow", "wide", "antipodal"])
+def test_reparam_winding_regimes(mods, k, regime):
+    # the winding sum is evaluated relative to the nearest winding (reparam_core.cuh): exercise the cases where that choice
+    # matters -- sharply peaked densities (a x ~ 1e4), angles beyond the last winding (the reference point is clamped to
+    # +-K), and angles next to pi where two windings carry the same weight
+    _, rp, _ = mods
+    torch.manual_seed(11)
+    B = 20011
+    mu = O.random_group_matrices(B, dtype=torch.float64)
+    eps = torch.randn(1, B, 3, dtype=torch.float64)
+    if regime == "narrow":
+        sigma = 0.005 + 0.045 * torch.rand(B, 3, dtype=torch.float64)
+    elif regime == "wide":
+        sigma = 3.0 + 17.0 * torch.rand(B, 3, dtype=torch.float64)            # theta up to ~ 100 > (2K+1) pi
+    else:
+        sigma = 0.3 + 2.0 * torch.rand(B, 3, dtype=torch.float64)
+        v = eps[0] * sigma
+        target = math.pi * (1 + 2 * torch.randint(0, 3, (B, 1)).double()) + 1e-3 * torch.randn(B, 1, dtype=torch.float64)
+        eps = (v / v.norm(dim=-1, keepdim=True) * target / sigma)[None]       # |eps * sigma| = (2j+1) pi + O(1e-3)
+    wz, wl = torch.randn(1, B, 3, 3, dtype=torch.float64), torch.randn(1, B, dtype=torch.float64)
+    z64, lq64, gmu64, gsg64 = oracle_reparam(mu, sigma, eps, k, wz, wl, torch.float64)
+    _, lq32, gmu32, gsg32 = oracle_reparam(mu, sigma, eps, k, wz, wl, torch.float32)
+    mug, sgg = mu.float().cuda().requires_grad_(True), sigma.float().cuda().requires_grad_(True)
+    z, lq = rp.so3_reparameterize(mug, sgg, eps.float().cuda(), k)
+    ((z * wz.float().cuda()).sum() + (lq * wl.float().cuda()).sum()).backward()
+    assert torch.isfinite(lq).all() and torch.isfinite(sgg.grad).all() and torch.isfinite(mug.grad).all()
+    as_good_as_ref32(lq, lq64, lq32, "log_q")
+    as_good_as_ref32(mug.grad, gmu64, gmu32, "g_mu")
+    as_good_as_ref32(sgg.grad, gsg64, gsg32, "g_sigma")
+    # float64 instantiation against the float64 oracle
+    mud, sgd = mu.cuda().requires_grad_(True), sigma.cuda().requires_grad_(True)
+    zd, lqd = rp.so3_reparameterize(mud, sgd, eps.cuda(), k)
+    ((zd * wz.cuda()).sum() + (lqd * wl.cuda()).sum()).backward()
+    scale = lambda t: max(1.0, float(t.abs().max()))                             # noqa: E731
+    assert (lqd.cpu() - lq64).abs().max().item() < 1e-9 * scale(lq64)
+    assert (sgd.grad.cpu() - gsg64).abs().max().item() < 1e-8 * scale(gsg64)
+    assert (mud.grad.cpu() - gmu64).abs().max().item() < 1e-8 * scale(gmu64)
+
+
 def test_reparam_multisample_broadcast(mods):
     # n > 1 with B not a multiple of anything: tiles wrap over the broadcast mu / sigma rows
     _, rp, _ = mods
@@ -120,6 +160,56 @@ def test_reparam_multisample_broadcast(mods):
     as_good_as_ref32(mug.grad, gmu64, gmu32, "g_mu")
     as_good_as_ref32(lq, lq64, lq32, "log_q")
     as_good_as_ref32(sgg.grad, gsg64, gsg32, "g_sigma")
+
+
+@pytest.mark.parametrize("n,B", [(1, 1024), (3, 1024), (3, 1028), (3, 1030), (2, 256), (5, 260), (1, 255), (1, 257)])
+@pytest.mark.parametrize("euler", [False, True])
+def test_reparam_tile_paths(mods, n, B, euler):
+    # full tiles move with TMA bulk copies, tiles that wrap over the broadcast rows / start on an unaligned broadcast row /
+    # are ragged, and tensors that are not 16-byte aligned, take the cp.async path: all must agree with the oracle, and
+    # an unaligned view of the same data must give bit-identical results
+    lt, rp, _ = mods
+    torch.manual_seed(5)
+    k = 3
+    mu = O.random_group_matrices(B, dtype=torch.float64)
+    # small sigma keeps theta away from 2 pi, where half an ulp of theta moves g_sigma by 1e-3 (1 / (2 - 2 cos theta) next
+    # to its clamp): this test is about tile handling, the ill-conditioned regimes are test_reparam_winding_regimes'
+    sigma = torch.nn.functional.softplus(torch.randn(B, 3, dtype=torch.float64) - 1.5)
+    eps = torch.randn(n, B, 3, dtype=torch.float64)
+    wz, wl = torch.randn(n, B, 3, 3, dtype=torch.float64), torch.randn(n, B, dtype=torch.float64)
+    z64, lq64, gmu64, gsg64 = oracle_reparam(mu, sigma, eps, k, wz, wl, torch.float64)
+    _, lq32, gmu32, gsg32 = oracle_reparam(mu, sigma, eps, k, wz, wl, torch.float32)
+
+    def shifted(t):          # same values, storage offset of one element: not 16-byte aligned
+        buf = torch.empty(t.numel() + 1, dtype=t.dtype, device=t.device)
+        buf[1:] = t.reshape(-1)
+        return buf[1:].view(t.shape)
+
+    def run(unaligned):
+        prep = shifted if unaligned else (lambda t: t)
+        mug, sgg = prep(mu.float().cuda()).requires_grad_(True), prep(sigma.float().cuda()).requires_grad_(True)
+        e = prep(eps.float().cuda())
+        if euler:
+            ang, lq = rp.so3_reparameterize_eazyz(mug, sgg, e, k)
+            wa = torch.randn(ang.shape, device="cuda", generator=torch.Generator("cuda").manual_seed(2))
+            ((ang * wa).sum() + (lq * wl.float().cuda()).sum()).backward()
+            return ang, lq, mug.grad, sgg.grad
+        z, lq = rp.so3_reparameterize(mug, sgg, e, k)
+        ((z * prep(wz.float().cuda())).sum() + (lq * wl.float().cuda()).sum()).backward()
+        return z, lq, mug.grad, sgg.grad
+
+    out, lq, gmu, gsg = run(False)
+    out_u, lq_u, gmu_u, gsg_u = run(True)
+    for a, b in ((out, out_u), (lq, lq_u), (gmu, gmu_u), (gsg, gsg_u)):
+        assert torch.equal(a, b)
+    as_good_as_ref32(lq, lq64, lq32, "log_q")
+    if not euler:
+        close(out, z64, RTOL, ATOL, "z")
+        as_good_as_ref32(gmu, gmu64, gmu32, "g_mu")
+        as_good_as_ref32(gsg, gsg64, gsg32, "g_sigma")
+    else:
+        z, _ = rp.so3_reparameterize(mu.float().cuda(), sigma.float().cuda(), eps.float().cuda(), k)
+        assert torch.equal(out, lt.group_matrix_to_eazyz(z))
 
 
 def test_reparam_full_size_properties(mods):
