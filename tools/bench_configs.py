@@ -147,3 +147,28 @@ def step_ps(i):
 
 
 row("configs[2] block_wigner_matrix_multiply fwd+bwd, per-sample spectrum (N,81,10)", timed(step_ps), N, 5 * 4 * M * C + 36)
+del specs, gs, angs
+torch.cuda.empty_cache()
+
+# ---- the elementwise lie_tools maps through the C ABI at 2^22 rows (each tensor set > L2, two
+# rotating sets); bytes = the map's inputs + outputs (forward), inputs + upstream gradient + input gradient (backward)
+R = 1 << 22
+mats = [lt.random_group_matrices(R, device=dev) for _ in range(2)]
+ROWOPS = [("rodrigues", 3, 9, lambda: torch.randn(R, 3, device=dev)),
+          ("log_map", 9, 9, None),
+          ("quat_to_mat", 4, 9, lambda: torch.randn(R, 4, device=dev)),
+          ("mat_to_quat", 9, 4, None),
+          ("quat_to_eazyz", 4, 3, lambda: torch.randn(R, 4, device=dev)),
+          ("mat_to_eazyz", 9, 3, None)]
+for name, wi, wo, gen in ROWOPS:
+    ins = mats if gen is None else [gen() for _ in range(2)]
+    out, gout, gin = torch.empty(R, wo, device=dev), torch.randn(R, wo, device=dev), torch.empty(R, wi, device=dev)
+
+    def f(i, name=name, ins=ins):
+        _cabi.call("lv_%s_fwd_f32" % name, p_(ins[i % 2]), p_(out), R, _stream())
+
+    def b(i, name=name, ins=ins):
+        _cabi.call("lv_%s_bwd_f32" % name, p_(ins[i % 2]), p_(gout), p_(gin), R, _stream())
+    row("8a lie_tools.%s forward, C ABI, 2^22 rows" % name, timed(f, iters=30), R, 4 * (wi + wo))
+    row("8a lie_tools.%s backward, C ABI, 2^22 rows" % name, timed(b, iters=30), R, 4 * (2 * wi + wo))
+    del ins, out, gout, gin
