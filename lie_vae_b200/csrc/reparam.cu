@@ -214,6 +214,140 @@ so3_reparam_bwd_kernel(const T* __restrict__ mu, const T* __restrict__ sigma, co
     }
 }
 
+// ------------------------------------------------------------------ persistent, double-buffered variants
+// Used when every tile can move with TMA bulk copies (16-byte aligned tensors; n == 1, or B a multiple of the tile so
+// that no tile wraps over the broadcast rows) and there are enough full tiles to keep every SM's resident CTAs busy for
+// several rounds.  A CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... through TWO sets of staging buffers:
+// thread 0 issues the bulk loads of the next tile before the CTA starts on the current one, so the load latency the
+// one-tile-per-CTA kernels expose at their barrier (ncu: 27 % of the stall samples) overlaps the arithmetic.
+//   iteration it, stage s = it & 1:   [thread 0] load(tile it+1 -> stage s^1)     -- stage s^1's previous store has been
+//                                     wait full[s] (parity (it >> 1) & 1)            read out (wait_group.read below)
+//                                     compute in place; fence.proxy.async; __syncthreads
+//                                     [thread 0] bulk store(stage s), commit, wait until the engine has read it
+// The ragged tail (total % TILE samples) is a separate launch of the kernels above.
+template <typename T, int TILE, bool EULER> struct RpFwdStage {
+    T m[TILE * 9];      // mu in, z out
+    T s[TILE * 3];
+    T e[TILE * 3];      // eps in, Euler angles out
+};
+template <typename T, int TILE, bool EULER> struct RpBwdStage {
+    T m[TILE * 9];
+    T g[TILE * 9];      // gz in, g_mu out
+    T s[TILE * 3];
+    T e[TILE * 3];      // eps in, g_sigma out
+    T a[EULER ? TILE * 3 : 4];   // g_angles in
+};
+
+template <typename T, int KT, bool EULER, int TILE>
+__global__ void __launch_bounds__(TILE)
+so3_reparam_fwd_pipe_kernel(const T* __restrict__ mu, const T* __restrict__ sigma, const T* __restrict__ eps,
+                            T* __restrict__ z, T* __restrict__ angles, T* __restrict__ log_q, int64_t ntiles,
+                            int64_t B, int krt) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using Stage = RpFwdStage<T, TILE, EULER>;
+    Stage* st = reinterpret_cast<Stage*>(smem_raw);
+    __shared__ __align__(8) uint64_t s_full[2];
+    const int t = threadIdx.x;
+    auto load = [&](int64_t tile, int s) {
+        const int64_t i0 = tile * TILE, b0 = i0 < B ? i0 : i0 % B;
+        mbar_expect_tx(&s_full[s], uint32_t(TILE * 15 * sizeof(T)));
+        tma_load(st[s].m, mu + b0 * 9, uint32_t(TILE * 9 * sizeof(T)), &s_full[s]);
+        tma_load(st[s].s, sigma + b0 * 3, uint32_t(TILE * 3 * sizeof(T)), &s_full[s]);
+        tma_load(st[s].e, eps + i0 * 3, uint32_t(TILE * 3 * sizeof(T)), &s_full[s]);
+    };
+    if (t == 0) {
+        mbar_init(&s_full[0], 1);
+        mbar_init(&s_full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (int64_t(blockIdx.x) < ntiles) load(blockIdx.x, 0);
+    }
+    __syncthreads();
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int s = it & 1;
+        if (t == 0 && tile + gridDim.x < ntiles) load(tile + gridDim.x, s ^ 1);
+        mbar_wait(&s_full[s], uint32_t(it >> 1) & 1u);
+        const int64_t i0 = tile * TILE;
+        T m[9], sg[3], ep[3], zr[9], e[3], lq;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) m[j] = st[s].m[t * 9 + j];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { sg[j] = st[s].s[t * 3 + j]; ep[j] = st[s].e[t * 3 + j]; }
+        reparam_sample_fwd<T, KT, EULER>(m, sg, ep, krt, log_q != nullptr, zr, e, &lq);
+#pragma unroll
+        for (int j = 0; j < 9; ++j) st[s].m[t * 9 + j] = zr[j];
+        if (EULER) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) st[s].e[t * 3 + j] = e[j];
+        }
+        if (log_q != nullptr) log_q[i0 + t] = lq;
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (t == 0) {
+            if (z != nullptr) tma_store(z + i0 * 9, st[s].m, uint32_t(TILE * 9 * sizeof(T)));
+            if (EULER) tma_store(angles + i0 * 3, st[s].e, uint32_t(TILE * 3 * sizeof(T)));
+            tma_store_commit_wait();
+        }
+    }
+}
+
+template <typename T, int KT, bool EULER, int TILE>
+__global__ void __launch_bounds__(TILE)
+so3_reparam_bwd_pipe_kernel(const T* __restrict__ mu, const T* __restrict__ sigma, const T* __restrict__ eps,
+                            const T* __restrict__ gz, const T* __restrict__ gangles, const T* __restrict__ glq,
+                            T* __restrict__ gmu, T* __restrict__ gsigma, int64_t ntiles, int64_t B, int krt) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using Stage = RpBwdStage<T, TILE, EULER>;
+    Stage* st = reinterpret_cast<Stage*>(smem_raw);
+    __shared__ __align__(8) uint64_t s_full[2];
+    const int t = threadIdx.x;
+    auto load = [&](int64_t tile, int s) {
+        const int64_t i0 = tile * TILE, b0 = i0 < B ? i0 : i0 % B;
+        mbar_expect_tx(&s_full[s], uint32_t(TILE * (15 + (gz != nullptr ? 9 : 0) + (EULER ? 3 : 0)) * sizeof(T)));
+        tma_load(st[s].m, mu + b0 * 9, uint32_t(TILE * 9 * sizeof(T)), &s_full[s]);
+        tma_load(st[s].s, sigma + b0 * 3, uint32_t(TILE * 3 * sizeof(T)), &s_full[s]);
+        tma_load(st[s].e, eps + i0 * 3, uint32_t(TILE * 3 * sizeof(T)), &s_full[s]);
+        if (gz != nullptr) tma_load(st[s].g, gz + i0 * 9, uint32_t(TILE * 9 * sizeof(T)), &s_full[s]);
+        if (EULER) tma_load(st[s].a, gangles + i0 * 3, uint32_t(TILE * 3 * sizeof(T)), &s_full[s]);
+    };
+    if (t == 0) {
+        mbar_init(&s_full[0], 1);
+        mbar_init(&s_full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (int64_t(blockIdx.x) < ntiles) load(blockIdx.x, 0);
+    }
+    __syncthreads();
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int s = it & 1;
+        if (t == 0 && tile + gridDim.x < ntiles) load(tile + gridDim.x, s ^ 1);
+        const int64_t i0 = tile * TILE;
+        const T gl = glq != nullptr ? glq[i0 + t] : T(0);
+        mbar_wait(&s_full[s], uint32_t(it >> 1) & 1u);
+        T m[9], G[9], sg[3], ep[3], ge[3] = {T(0), T(0), T(0)}, gm[9], gsg[3];
+#pragma unroll
+        for (int j = 0; j < 9; ++j) { m[j] = st[s].m[t * 9 + j]; G[j] = gz != nullptr ? st[s].g[t * 9 + j] : T(0); }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { sg[j] = st[s].s[t * 3 + j]; ep[j] = st[s].e[t * 3 + j]; }
+        if (EULER) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) ge[j] = st[s].a[t * 3 + j];
+        }
+        reparam_sample_bwd<T, KT, EULER>(m, sg, ep, G, ge, gl, glq != nullptr, krt, gm, gsg);
+#pragma unroll
+        for (int j = 0; j < 9; ++j) st[s].g[t * 9 + j] = gm[j];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) st[s].e[t * 3 + j] = gsg[j];
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (t == 0) {
+            tma_store(gmu + i0 * 9, st[s].g, uint32_t(TILE * 9 * sizeof(T)));
+            tma_store(gsigma + i0 * 3, st[s].e, uint32_t(TILE * 3 * sizeof(T)));
+            tma_store_commit_wait();
+        }
+    }
+}
+
 }  // namespace lv
 
 // ====================================================================== C ABI
@@ -229,6 +363,79 @@ static int aligned16(const P*... p) {
     return (((reinterpret_cast<uintptr_t>(p)) | ...) & 15u) == 0;
 }
 
+// persistent launch geometry: the CTAs that are resident at once, trimmed so that every CTA walks the same number of
+// tiles (a partial last round would leave most SMs idle for one tile time); 0 = use the one-tile-per-CTA kernels
+template <typename K>
+static int pipe_grid(K kernel, int threads, size_t smem, int64_t ntiles, int* grid) {
+    *grid = 0;
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e == cudaSuccess && smem > 48 * 1024) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
+    if (e != cudaSuccess) { lv::set_error("so3_reparam: launch geometry query failed (%s)", cudaGetErrorString(e)); return int(e); }
+    const int64_t cap = int64_t(sms) * per_sm;
+    if (cap < 1 || ntiles < 2 * cap) return LV_OK;          // too few tiles to pipeline: one tile per CTA
+    const int64_t rounds = (ntiles + cap - 1) / cap;
+    *grid = int((ntiles + rounds - 1) / rounds);
+    return LV_OK;
+}
+
+template <typename T, int KT, bool EULER, int TILE>
+static int reparam_fwd_launch(const T* mu, const T* sigma, const T* eps, T* z, T* angles, T* log_q, int64_t n, int64_t B, int k,
+                              cudaStream_t st) {
+    const int64_t total = n * B;
+    const int al = aligned16(mu, sigma, eps, z, angles);      // null pointers count as aligned
+    int64_t done = 0;
+    if (al && (n == 1 || B % TILE == 0)) {
+        constexpr size_t SMEM = 2 * sizeof(lv::RpFwdStage<T, TILE, EULER>);
+        const int64_t nfull = total / TILE;
+        int grid = 0;
+        int rc = pipe_grid(lv::so3_reparam_fwd_pipe_kernel<T, KT, EULER, TILE>, TILE, SMEM, nfull, &grid);
+        if (rc) return rc;
+        if (grid > 0) {
+            lv::so3_reparam_fwd_pipe_kernel<T, KT, EULER, TILE><<<grid, TILE, SMEM, st>>>(mu, sigma, eps, z, angles, log_q, nfull, B, k);
+            done = nfull * TILE;                              // the ragged tail (n == 1 only) follows below
+        }
+    }
+    if (done < total) {
+        const int64_t rest = total - done;                    // done > 0 implies n == 1: the tail is its own (B = rest) problem
+        const unsigned grid = unsigned((rest + TILE - 1) / TILE);
+        lv::so3_reparam_fwd_kernel<T, KT, EULER, TILE><<<grid, TILE, 0, st>>>(
+            mu + (done ? done * 9 : 0), sigma + (done ? done * 3 : 0), eps + done * 3, z ? z + done * 9 : nullptr,
+            angles ? angles + done * 3 : nullptr, log_q ? log_q + done : nullptr, rest, done ? rest : B, k, al);
+    }
+    return LV_OK;
+}
+
+template <typename T, int KT, bool EULER, int TILE>
+static int reparam_bwd_launch(const T* mu, const T* sigma, const T* eps, const T* gz, const T* gangles, const T* glq, T* gmu,
+                              T* gsigma, int64_t n, int64_t B, int k, cudaStream_t st) {
+    const int64_t total = n * B;
+    const int al = aligned16(mu, sigma, eps, gz, gangles, gmu, gsigma);
+    int64_t done = 0;
+    if (al && (n == 1 || B % TILE == 0)) {
+        constexpr size_t SMEM = 2 * sizeof(lv::RpBwdStage<T, TILE, EULER>);
+        const int64_t nfull = total / TILE;
+        int grid = 0;
+        int rc = pipe_grid(lv::so3_reparam_bwd_pipe_kernel<T, KT, EULER, TILE>, TILE, SMEM, nfull, &grid);
+        if (rc) return rc;
+        if (grid > 0) {
+            lv::so3_reparam_bwd_pipe_kernel<T, KT, EULER, TILE><<<grid, TILE, SMEM, st>>>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, nfull, B, k);
+            done = nfull * TILE;
+        }
+    }
+    if (done < total) {
+        const int64_t rest = total - done;
+        const unsigned grid = unsigned((rest + TILE - 1) / TILE);
+        lv::so3_reparam_bwd_kernel<T, KT, EULER, TILE><<<grid, TILE, 0, st>>>(
+            mu + (done ? done * 9 : 0), sigma + (done ? done * 3 : 0), eps + done * 3, gz ? gz + done * 9 : nullptr,
+            gangles ? gangles + done * 3 : nullptr, glq ? glq + done : nullptr, gmu + done * 9, gsigma + done * 3, rest,
+            done ? rest : B, k, al);
+    }
+    return LV_OK;
+}
+
 template <typename T, bool EULER>
 static int reparam_fwd(const char* name, const T* mu, const T* sigma, const T* eps, T* z, T* angles,
                        T* log_q, int64_t n, int64_t B, int k, void* stream) {
@@ -239,12 +446,11 @@ static int reparam_fwd(const char* name, const T* mu, const T* sigma, const T* e
     if (!mu || !sigma || !eps || (EULER ? !angles : !z)) { lv::set_error("%s: null pointer", name); return LV_ERR_ARG; }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     constexpr int TILE = sizeof(T) == 8 ? lv::RP_TILE / 2 : lv::RP_TILE;
-    const unsigned grid = unsigned((total + TILE - 1) / TILE);
-    const int al = aligned16(mu, sigma, eps, z, angles);      // null pointers count as aligned
-    if constexpr (sizeof(T) == 8) lv::so3_reparam_fwd_kernel<T, 0, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, z, angles, log_q, total, B, k, al);
-    else if (k == 3) lv::so3_reparam_fwd_kernel<T, 3, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, z, angles, log_q, total, B, k, al);
-    else if (k == 10) lv::so3_reparam_fwd_kernel<T, 10, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, z, angles, log_q, total, B, k, al);
-    else lv::so3_reparam_fwd_kernel<T, 0, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, z, angles, log_q, total, B, k, al);
+    if constexpr (sizeof(T) == 8) rc = reparam_fwd_launch<T, 0, EULER, TILE>(mu, sigma, eps, z, angles, log_q, n, B, k, st);
+    else if (k == 3) rc = reparam_fwd_launch<T, 3, EULER, TILE>(mu, sigma, eps, z, angles, log_q, n, B, k, st);
+    else if (k == 10) rc = reparam_fwd_launch<T, 10, EULER, TILE>(mu, sigma, eps, z, angles, log_q, n, B, k, st);
+    else rc = reparam_fwd_launch<T, 0, EULER, TILE>(mu, sigma, eps, z, angles, log_q, n, B, k, st);
+    if (rc) return rc;
     return lv::check_launch(name);
 }
 
@@ -259,12 +465,11 @@ static int reparam_bwd(const char* name, const T* mu, const T* sigma, const T* e
     if (!mu || !sigma || !eps || !gmu || !gsigma || (EULER && !gangles)) { lv::set_error("%s: null pointer", name); return LV_ERR_ARG; }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     constexpr int TILE = sizeof(T) == 8 ? lv::RP_TILE / 2 : lv::RP_TILE;
-    const unsigned grid = unsigned((total + TILE - 1) / TILE);
-    const int al = aligned16(mu, sigma, eps, gz, gangles, gmu, gsigma);
-    if constexpr (sizeof(T) == 8) lv::so3_reparam_bwd_kernel<T, 0, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, total, B, k, al);
-    else if (k == 3) lv::so3_reparam_bwd_kernel<T, 3, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, total, B, k, al);
-    else if (k == 10) lv::so3_reparam_bwd_kernel<T, 10, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, total, B, k, al);
-    else lv::so3_reparam_bwd_kernel<T, 0, EULER, TILE><<<grid, TILE, 0, st>>>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, total, B, k, al);
+    if constexpr (sizeof(T) == 8) rc = reparam_bwd_launch<T, 0, EULER, TILE>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, n, B, k, st);
+    else if (k == 3) rc = reparam_bwd_launch<T, 3, EULER, TILE>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, n, B, k, st);
+    else if (k == 10) rc = reparam_bwd_launch<T, 10, EULER, TILE>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, n, B, k, st);
+    else rc = reparam_bwd_launch<T, 0, EULER, TILE>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, n, B, k, st);
+    if (rc) return rc;
     return lv::check_launch(name);
 }
 
