@@ -220,10 +220,14 @@ so3_reparam_bwd_kernel(const T* __restrict__ mu, const T* __restrict__ sigma, co
 // several rounds.  A CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... through TWO sets of staging buffers:
 // thread 0 issues the bulk loads of the next tile before the CTA starts on the current one, so the load latency the
 // one-tile-per-CTA kernels expose at their barrier (ncu: 27 % of the stall samples) overlaps the arithmetic.
-//   iteration it, stage s = it & 1:   [thread 0] load(tile it+1 -> stage s^1)     -- stage s^1's previous store has been
-//                                     wait full[s] (parity (it >> 1) & 1)            read out (wait_group.read below)
+//   iteration it, stage s = it % NS:  [thread 0] wait until the store issued from stage (it+1) % NS has been read out
+//                                                (NS = 2: the previous iteration's; NS = 3: the one before, a full
+//                                                iteration of slack), then load(tile it+1 -> stage (it+1) % NS)
+//                                     wait full[s] (parity (it / NS) & 1)
 //                                     compute in place; fence.proxy.async; __syncthreads
-//                                     [thread 0] bulk store(stage s), commit, wait until the engine has read it
+//                                     [thread 0] bulk store(stage s), commit
+// Forward: three stages (45 KB) -- with two, thread 0 waits for its store right after issuing it and the other 255
+// threads wait for thread 0 at the next barrier; backward: two stages (55 KB; a third would cost a resident CTA).
 // The ragged tail (total % TILE samples) is a separate launch of the kernels above.
 template <typename T, int TILE, bool EULER> struct RpFwdStage {
     T m[TILE * 9];      // mu in, z out
@@ -238,7 +242,7 @@ template <typename T, int TILE, bool EULER> struct RpBwdStage {
     T a[EULER ? TILE * 3 : 4];   // g_angles in
 };
 
-template <typename T, int KT, bool EULER, int TILE>
+template <typename T, int KT, bool EULER, int TILE, int NS>
 __global__ void __launch_bounds__(TILE)
 so3_reparam_fwd_pipe_kernel(const T* __restrict__ mu, const T* __restrict__ sigma, const T* __restrict__ eps,
                             T* __restrict__ z, T* __restrict__ angles, T* __restrict__ log_q, int64_t ntiles,
@@ -246,7 +250,7 @@ so3_reparam_fwd_pipe_kernel(const T* __restrict__ mu, const T* __restrict__ sigm
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Stage = RpFwdStage<T, TILE, EULER>;
     Stage* st = reinterpret_cast<Stage*>(smem_raw);
-    __shared__ __align__(8) uint64_t s_full[2];
+    __shared__ __align__(8) uint64_t s_full[NS];
     const int t = threadIdx.x;
     auto load = [&](int64_t tile, int s) {
         const int64_t i0 = tile * TILE, b0 = i0 < B ? i0 : i0 % B;
@@ -256,17 +260,20 @@ so3_reparam_fwd_pipe_kernel(const T* __restrict__ mu, const T* __restrict__ sigm
         tma_load(st[s].e, eps + i0 * 3, uint32_t(TILE * 3 * sizeof(T)), &s_full[s]);
     };
     if (t == 0) {
-        mbar_init(&s_full[0], 1);
-        mbar_init(&s_full[1], 1);
+#pragma unroll
+        for (int q = 0; q < NS; ++q) mbar_init(&s_full[q], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (int64_t(blockIdx.x) < ntiles) load(blockIdx.x, 0);
     }
     __syncthreads();
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const int s = it & 1;
-        if (t == 0 && tile + gridDim.x < ntiles) load(tile + gridDim.x, s ^ 1);
-        mbar_wait(&s_full[s], uint32_t(it >> 1) & 1u);
+        const int s = it % NS;
+        if (t == 0 && tile + gridDim.x < ntiles) {
+            tma_store_wait_read<NS - 2>();
+            load(tile + gridDim.x, (it + 1) % NS);
+        }
+        mbar_wait(&s_full[s], uint32_t(it / NS) & 1u);
         const int64_t i0 = tile * TILE;
         T m[9], sg[3], ep[3], zr[9], e[3], lq;
 #pragma unroll
@@ -286,12 +293,13 @@ so3_reparam_fwd_pipe_kernel(const T* __restrict__ mu, const T* __restrict__ sigm
         if (t == 0) {
             if (z != nullptr) tma_store(z + i0 * 9, st[s].m, uint32_t(TILE * 9 * sizeof(T)));
             if (EULER) tma_store(angles + i0 * 3, st[s].e, uint32_t(TILE * 3 * sizeof(T)));
-            tma_store_commit_wait();
+            tma_store_commit();
         }
     }
+    if (t == 0) tma_store_wait_read<0>();      // the staging buffers stay valid until the copy engine has read them
 }
 
-template <typename T, int KT, bool EULER, int TILE>
+template <typename T, int KT, bool EULER, int TILE, int NS>
 __global__ void __launch_bounds__(TILE)
 so3_reparam_bwd_pipe_kernel(const T* __restrict__ mu, const T* __restrict__ sigma, const T* __restrict__ eps,
                             const T* __restrict__ gz, const T* __restrict__ gangles, const T* __restrict__ glq,
@@ -299,7 +307,7 @@ so3_reparam_bwd_pipe_kernel(const T* __restrict__ mu, const T* __restrict__ sigm
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Stage = RpBwdStage<T, TILE, EULER>;
     Stage* st = reinterpret_cast<Stage*>(smem_raw);
-    __shared__ __align__(8) uint64_t s_full[2];
+    __shared__ __align__(8) uint64_t s_full[NS];
     const int t = threadIdx.x;
     auto load = [&](int64_t tile, int s) {
         const int64_t i0 = tile * TILE, b0 = i0 < B ? i0 : i0 % B;
@@ -311,19 +319,22 @@ so3_reparam_bwd_pipe_kernel(const T* __restrict__ mu, const T* __restrict__ sigm
         if (EULER) tma_load(st[s].a, gangles + i0 * 3, uint32_t(TILE * 3 * sizeof(T)), &s_full[s]);
     };
     if (t == 0) {
-        mbar_init(&s_full[0], 1);
-        mbar_init(&s_full[1], 1);
+#pragma unroll
+        for (int q = 0; q < NS; ++q) mbar_init(&s_full[q], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (int64_t(blockIdx.x) < ntiles) load(blockIdx.x, 0);
     }
     __syncthreads();
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const int s = it & 1;
-        if (t == 0 && tile + gridDim.x < ntiles) load(tile + gridDim.x, s ^ 1);
+        const int s = it % NS;
+        if (t == 0 && tile + gridDim.x < ntiles) {
+            tma_store_wait_read<NS - 2>();
+            load(tile + gridDim.x, (it + 1) % NS);
+        }
         const int64_t i0 = tile * TILE;
         const T gl = glq != nullptr ? glq[i0 + t] : T(0);
-        mbar_wait(&s_full[s], uint32_t(it >> 1) & 1u);
+        mbar_wait(&s_full[s], uint32_t(it / NS) & 1u);
         T m[9], G[9], sg[3], ep[3], ge[3] = {T(0), T(0), T(0)}, gm[9], gsg[3];
 #pragma unroll
         for (int j = 0; j < 9; ++j) { m[j] = st[s].m[t * 9 + j]; G[j] = gz != nullptr ? st[s].g[t * 9 + j] : T(0); }
@@ -343,9 +354,10 @@ so3_reparam_bwd_pipe_kernel(const T* __restrict__ mu, const T* __restrict__ sigm
         if (t == 0) {
             tma_store(gmu + i0 * 9, st[s].g, uint32_t(TILE * 9 * sizeof(T)));
             tma_store(gsigma + i0 * 3, st[s].e, uint32_t(TILE * 3 * sizeof(T)));
-            tma_store_commit_wait();
+            tma_store_commit();
         }
     }
+    if (t == 0) tma_store_wait_read<0>();      // the staging buffers stay valid until the copy engine has read them
 }
 
 }  // namespace lv
@@ -364,17 +376,25 @@ static int aligned16(const P*... p) {
 }
 
 // persistent launch geometry: the CTAs that are resident at once, trimmed so that every CTA walks the same number of
-// tiles (a partial last round would leave most SMs idle for one tile time); 0 = use the one-tile-per-CTA kernels
+// tiles (a partial last round would leave most SMs idle for one tile time); 0 = use the one-tile-per-CTA kernels.
+// `cap_cache` (one array per kernel instantiation, indexed by device) keeps SMs x resident CTAs after the first launch on
+// a device: the occupancy query and the shared-memory opt-in cost ~10 us of host time, as much as a small launch.
+constexpr int RP_MAX_DEVICES = 64;
 template <typename K>
-static int pipe_grid(K kernel, int threads, size_t smem, int64_t ntiles, int* grid) {
+static int pipe_grid(K kernel, int threads, size_t smem, int64_t ntiles, int* cap_cache, int* grid) {
     *grid = 0;
-    int dev = 0, sms = 0, per_sm = 0;
+    int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
-    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e == cudaSuccess && smem > 48 * 1024) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
-    if (e != cudaSuccess) { lv::set_error("so3_reparam: launch geometry query failed (%s)", cudaGetErrorString(e)); return int(e); }
-    const int64_t cap = int64_t(sms) * per_sm;
+    int64_t cap = (e == cudaSuccess && dev >= 0 && dev < RP_MAX_DEVICES) ? cap_cache[dev] : 0;
+    if (cap == 0) {
+        int sms = 0, per_sm = 0;
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e == cudaSuccess && smem > 48 * 1024) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
+        if (e != cudaSuccess) { lv::set_error("so3_reparam: launch geometry query failed (%s)", cudaGetErrorString(e)); return int(e); }
+        cap = int64_t(sms) * per_sm;
+        if (cap > 0 && dev >= 0 && dev < RP_MAX_DEVICES) cap_cache[dev] = int(cap);
+    }
     if (cap < 1 || ntiles < 2 * cap) return LV_OK;          // too few tiles to pipeline: one tile per CTA
     const int64_t rounds = (ntiles + cap - 1) / cap;
     *grid = int((ntiles + rounds - 1) / rounds);
@@ -388,13 +408,15 @@ static int reparam_fwd_launch(const T* mu, const T* sigma, const T* eps, T* z, T
     const int al = aligned16(mu, sigma, eps, z, angles);      // null pointers count as aligned
     int64_t done = 0;
     if (al && (n == 1 || B % TILE == 0)) {
-        constexpr size_t SMEM = 2 * sizeof(lv::RpFwdStage<T, TILE, EULER>);
+        constexpr int NS = 3;
+        constexpr size_t SMEM = NS * sizeof(lv::RpFwdStage<T, TILE, EULER>);
         const int64_t nfull = total / TILE;
+        static int cap_cache[RP_MAX_DEVICES] = {0};
         int grid = 0;
-        int rc = pipe_grid(lv::so3_reparam_fwd_pipe_kernel<T, KT, EULER, TILE>, TILE, SMEM, nfull, &grid);
+        int rc = pipe_grid(lv::so3_reparam_fwd_pipe_kernel<T, KT, EULER, TILE, NS>, TILE, SMEM, nfull, cap_cache, &grid);
         if (rc) return rc;
         if (grid > 0) {
-            lv::so3_reparam_fwd_pipe_kernel<T, KT, EULER, TILE><<<grid, TILE, SMEM, st>>>(mu, sigma, eps, z, angles, log_q, nfull, B, k);
+            lv::so3_reparam_fwd_pipe_kernel<T, KT, EULER, TILE, NS><<<grid, TILE, SMEM, st>>>(mu, sigma, eps, z, angles, log_q, nfull, B, k);
             done = nfull * TILE;                              // the ragged tail (n == 1 only) follows below
         }
     }
@@ -415,13 +437,15 @@ static int reparam_bwd_launch(const T* mu, const T* sigma, const T* eps, const T
     const int al = aligned16(mu, sigma, eps, gz, gangles, gmu, gsigma);
     int64_t done = 0;
     if (al && (n == 1 || B % TILE == 0)) {
-        constexpr size_t SMEM = 2 * sizeof(lv::RpBwdStage<T, TILE, EULER>);
+        constexpr int NS = 2;
+        constexpr size_t SMEM = NS * sizeof(lv::RpBwdStage<T, TILE, EULER>);
         const int64_t nfull = total / TILE;
+        static int cap_cache[RP_MAX_DEVICES] = {0};
         int grid = 0;
-        int rc = pipe_grid(lv::so3_reparam_bwd_pipe_kernel<T, KT, EULER, TILE>, TILE, SMEM, nfull, &grid);
+        int rc = pipe_grid(lv::so3_reparam_bwd_pipe_kernel<T, KT, EULER, TILE, NS>, TILE, SMEM, nfull, cap_cache, &grid);
         if (rc) return rc;
         if (grid > 0) {
-            lv::so3_reparam_bwd_pipe_kernel<T, KT, EULER, TILE><<<grid, TILE, SMEM, st>>>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, nfull, B, k);
+            lv::so3_reparam_bwd_pipe_kernel<T, KT, EULER, TILE, NS><<<grid, TILE, SMEM, st>>>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, nfull, B, k);
             done = nfull * TILE;
         }
     }
