@@ -148,7 +148,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_RESULT_OUT, flush=True)
 
 
 def workload_config(n_gpus):
@@ -402,9 +402,12 @@ def run_ours(args):
                                     "sample": "%d samples (bounded sample of the workload), best of 3 after 1 warm-up, torch CPU fp32" % sample}
         else:
             line["cpu_baseline"] = None
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+_RESULT_OUT = sys.stdout
 
 
 def main():
@@ -419,6 +422,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="plain launches instead of replaying a CUDA graph of the rank-local step")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON result: anything a library writes to file descriptor 1 (NCCL prints its
+    # version banner there) is sent to stderr, and the result goes to the saved descriptor
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
