@@ -69,14 +69,20 @@ def last_error():
     return msg.decode() if msg else ""
 
 
+_fn_cache = {}
+
+
 def call(name, *args):
     """Invoke an int-returning entry point; raise RuntimeError on a non-zero status."""
-    rc = getattr(lib(), name)(*args)
+    fn = _fn_cache.get(name)
+    if fn is None:
+        fn = _fn_cache[name] = getattr(lib(), name)
+    rc = fn(*args)
     if rc != 0:
         kind = "argument error" if rc < 0 else "CUDA error"
         raise RuntimeError("%s failed (%s %d): %s" % (name, kind, rc, last_error()))
 
 
 def ptr(t):
-    """Device pointer of a tensor (None -> NULL)."""
-    return None if t is None else ctypes.c_void_p(t.data_ptr())
+    """Device pointer of a tensor (None -> NULL) as the plain integer ctypes converts to ``void*``."""
+    return None if t is None else t.data_ptr()
