@@ -113,7 +113,10 @@ int lv_logsumexp_leading_bwd_f64(const double* in, const double* out, const doub
  *   SO3reparameterize.log_posterior reparameterize.py:233-263 + utils.logsumexp utils.py:4-26.
  *   mu (B,9), sigma (B,3) broadcast over n; eps (n,B,3); z (n,B,9); log_q (n,B) or NULL to skip.
  *   Backward: gz (n,B,9) or NULL (=0), glq (n,B) or NULL (=0); writes PER-SAMPLE gradients
- *   gmu (n,B,9), gsigma (n,B,3) -- for n > 1 reduce with lv_sum_leading_f32. ---- */
+ *   gmu (n,B,9), gsigma (n,B,3) -- for n > 1 reduce with lv_sum_leading_f32.
+ *   Any 4-byte (f64: 8-byte) aligned pointers are accepted; when every tensor is 16-byte aligned full tiles move with
+ *   TMA bulk copies and large launches (n == 1, or B a multiple of 256 [f64: 128]) run the persistent pipelined
+ *   kernels -- same results to rounding, about 1.3x faster. ---- */
 int lv_so3_reparam_fwd_f32(const float* mu, const float* sigma, const float* eps, float* z, float* log_q,
                            int64_t n, int64_t B, int k, void* stream);
 int lv_so3_reparam_bwd_f32(const float* mu, const float* sigma, const float* eps, const float* gz, const float* glq,
@@ -128,7 +131,7 @@ int lv_so3_reparam_eazyz_bwd_f32(const float* mu, const float* sigma, const floa
                                  const float* gangles, const float* glq, float* gmu, float* gsigma, int64_t n, int64_t B,
                                  int k, void* stream);
 
-/* float64 instantiations of the four entry points above (same contract; the winding terms use the library log/exp) */
+/* float64 instantiations of the four entry points above (same contract; the winding terms use the library exp) */
 int lv_so3_reparam_fwd_f64(const double* mu, const double* sigma, const double* eps, double* z, double* log_q,
                            int64_t n, int64_t B, int k, void* stream);
 int lv_so3_reparam_bwd_f64(const double* mu, const double* sigma, const double* eps, const double* gz, const double* glq,
