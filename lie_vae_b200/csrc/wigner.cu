@@ -44,6 +44,7 @@
 //
 // transpose=True (lie_tools.py:249-250): D^T = X(-c) J X(-b) J X(-a), i.e. the same kernels on
 // the angles (-c, -b, -a), with the angle gradients mapped back.
+#include <stdlib.h>
 #include "common.cuh"
 #include "wigner_gen.cuh"
 
@@ -662,6 +663,52 @@ static int launch_bwd_ws(const WgGeom& g, const float* angles, const float* spec
     return check_launch("wigner_reduce_partials");
 }
 
+#include "wigner_bwd_dg.cuh"
+
+// ---- degree-specialised backward (shared spectrum, C = 10, degrees 0..8 or 0..6, 16-byte aligned g_y, N >= 2) ------
+// LV_WIGNER_BWD=ws in the environment selects the first TMA-fed kernel instead (A/B measurements on one box).
+static bool dg_bwd_enabled() {
+    static const int on = [] { const char* e = getenv("LV_WIGNER_BWD"); return (e && e[0] == 'w') ? 0 : 1; }();
+    return on != 0;
+}
+static bool dg_bwd_eligible(int C, int lmin, int lmax, const float* gout, int64_t N) {
+    return dg_bwd_enabled() && C == 10 && lmin == 0 && (lmax == 8 || lmax == 6) && N >= 2 && (reinterpret_cast<uintptr_t>(gout) & 15u) == 0;
+}
+
+template <class CFG>
+static int launch_bwd_dg(const WgGeom& g, const float* angles, const float* spectrum, const float* gout, float* gangles,
+                         float* gspectrum, float* workspace, int64_t workspace_floats, int64_t N, int transpose, int accumulate,
+                         cudaStream_t st) {
+    using G = dg::Geo<CFG>;
+    constexpr int MC = G::MC, S = CFG::S;
+    if (!workspace || workspace_floats < ws_bwd_workspace_rows(g.sms) * MC) {
+        set_error("wigner_apply_bwd: workspace of %lld floats required", (long long)(ws_bwd_workspace_rows(g.sms) * MC));
+        return LV_ERR_ARG;
+    }
+    // bulk copies move multiples of 16 bytes = an even number of 4*MC-byte rows: an odd last sample goes to the generic kernel
+    const int64_t n_main = N & ~int64_t(1), n_tail = N - n_main;
+    const int64_t ntiles = (n_main + S - 1) / S;
+    const int last_rows = int(n_main - (ntiles - 1) * S);
+    const int grid = int(ntiles < g.sms ? ntiles : g.sms);
+    int rc = opt_in_smem(dg::wigner_bwd_dg_kernel<CFG>, G::SMEM);
+    if (rc) return rc;
+    float* partial = workspace;      // one row per CTA, then the tail's row
+    dg::wigner_bwd_dg_kernel<CFG><<<grid, G::THREADS, G::SMEM, st>>>(angles, spectrum, gout, gangles, partial, ntiles, last_rows, transpose);
+    if ((rc = check_launch("wigner_apply_bwd (dg)"))) return rc;
+    int rows = grid;
+    if (n_tail > 0) {
+        WgGeom gt = g;
+        gt.ntiles = (n_tail + g.S - 1) / g.S;
+        int tail_grid = 0;
+        rc = launch_bwd<true, 0, -1>(gt, angles + n_main * 3, spectrum, gout + n_main * MC, gangles + n_main * 3, nullptr,
+                                     partial + int64_t(rows) * MC, int64_t(gt.ntiles) * MC, n_tail, 0, CFG::LT, 10, transpose, st, &tail_grid);
+        if (rc) return rc;
+        rows += tail_grid;
+    }
+    wigner_reduce_partials<<<(MC + 31) / 32, dim3(32, 8), 0, st>>>(partial, gspectrum, rows, MC, accumulate);
+    return check_launch("wigner_reduce_partials");
+}
+
 }  // namespace lv
 
 // compile-time specialisations: 10 channels (ActionNet default, decoders.py:11 / main.py:168) with degrees
@@ -677,7 +724,7 @@ extern "C" int64_t lv_wigner_bwd_workspace_floats(int64_t N, int lmin, int lmax,
     if (lv::wigner_geometry("wigner_bwd_workspace", N, lmin, lmax, C, true, g) != LV_OK) return -1;
     const int64_t cap = int64_t(g.sms) * lv::WG_MAX_CTAS_PER_SM;
     int64_t rows = g.ntiles < cap ? g.ntiles : cap;
-    if (C == 10 && lmin == 0 && (lmax == 8 || lmax == 6) && N >= lv::WD_S) {
+    if (C == 10 && lmin == 0 && (lmax == 8 || lmax == 6) && N >= 2) {
         const int64_t tma_rows = lv::ws_bwd_workspace_rows(g.sms);
         if (tma_rows > rows) rows = tma_rows;
     }
@@ -715,6 +762,10 @@ extern "C" int lv_wigner_apply_bwd_f32(const float* angles, const float* spectru
     }
     if (!angles || !spectrum || !gout || !gangles) { lv::set_error("wigner_apply_bwd: null pointer"); return LV_ERR_ARG; }
     int grid = 0;
+    if (shared_spectrum && lv::dg_bwd_eligible(C, lmin, lmax, gout, N)) {
+        if (lmax == 8) return lv::launch_bwd_dg<lv::dg::LV_DG_CFG8>(g, angles, spectrum, gout, gangles, gspectrum, workspace, workspace_floats, N, transpose, accumulate, st);
+        return lv::launch_bwd_dg<lv::dg::Cfg6A>(g, angles, spectrum, gout, gangles, gspectrum, workspace, workspace_floats, N, transpose, accumulate, st);
+    }
     if (shared_spectrum && lv::ws_bwd_eligible(C, lmin, lmax, gout, N)) {
         if (lmax == 8) return lv::launch_bwd_ws<8>(g, angles, spectrum, gout, gangles, gspectrum, workspace, workspace_floats, N, transpose, accumulate, st);
         return lv::launch_bwd_ws<6>(g, angles, spectrum, gout, gangles, gspectrum, workspace, workspace_floats, N, transpose, accumulate, st);

@@ -456,11 +456,12 @@ def test_wigner_errors(mods):
 
 
 @pytest.mark.parametrize("L", [8, 6])
-@pytest.mark.parametrize("N", [16, 17, 31, 48, 49, 16 * 150 + 3, 16 * 600])
+@pytest.mark.parametrize("N", [2, 3, 11, 12, 13, 16, 17, 31, 48, 49, 12 * 148 + 2, 16 * 150 + 3, 16 * 600, 12 * 148 * 6 + 10])
 @pytest.mark.parametrize("tr", [False, True])
 def test_ws_backward_matches_cp_async_backward(mods, L, N, tr):
-    """The warp-decoupled TMA-fed backward (C = 10, degrees 0..8 / 0..6, 16-byte aligned g_y) against the cp.async kernel, which
-    the same call falls back to when g_y is only 4-byte aligned; and against the oracle for the small sizes."""
+    """The degree-specialised TMA-fed backward (C = 10, degrees 0..8 / 0..6, 16-byte aligned g_y; 12-sample tiles, ragged last
+    tile, odd last sample) against the cp.async kernel, which the same call falls back to when g_y is only 4-byte aligned;
+    and against the oracle for the small sizes."""
     from lie_vae_b200 import _ops
     torch.manual_seed(N + L)
     M, C = (L + 1) ** 2, 10
@@ -492,9 +493,9 @@ def test_ws_backward_matches_cp_async_backward(mods, L, N, tr):
 
 
 def test_ws_backward_stress_reproducible(mods):
-    """Many back-to-back launches of the warp-decoupled backward (persistent CTAs, math warps pulling slices from a work
-    counter, producer warps recycling 4 mbarrier-tracked tile buffers per SM): every launch must reproduce the first one
-    bit for bit, whichever warp computed which slice.  Guards the full/empty hand-over protocol."""
+    """Many back-to-back launches of the degree-specialised backward (persistent CTAs, math warps bound to degree groups,
+    producer warps recycling the mbarrier-tracked tile ring): every launch must reproduce the first one bit for bit.
+    Guards the full/empty hand-over protocol."""
     from lie_vae_b200 import _ops
     torch.manual_seed(5)
     N, L, C = 1 << 17, 8, 10

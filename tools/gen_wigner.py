@@ -197,6 +197,28 @@ def emit(l, ktab):
     if n_gen == 0:
         o.append("        (void)g; (void)s; (void)tx; (void)ty;")
     o.append("    }")
+    # ---- U_k = G_k s, k = x, y, z, as packed vectors: for a spectrum shared by every sample they are computed once per
+    #      thread, and the generator forms become plain dot products T_k = <g_s, U_k> (wigner_bwd_dg.cuh)
+    o.append("    static __device__ __forceinline__ void gvecs(const Vec& s, Vec& ux, Vec& uy, Vec& uz) {")
+    for name, G in (("x", Gx), ("y", Gy), ("z", Gz)):
+        for i in range(n):
+            terms = [(j, G[i, j]) for j in range(n) if abs(G[i, j]) > 1e-12]
+            if not terms:
+                e = "0.0f"
+            else:
+                e = "%s * %s" % (lit(terms[0][1]), d.acc(terms[0][0], "s"))
+                for j, v in terms[1:]:
+                    e = "fmaf(%s, %s, %s)" % (lit(v), d.acc(j, "s"), e)
+            o.append("        const float %s%d = %s;" % (name, i, e))
+        for q, (m1, m2) in enumerate(d.pairs):
+            o.append("        u%s.lo[%d] = pk(%s%d, %s%d); u%s.hi[%d] = pk(%s%d, %s%d);"
+                     % (name, q, name, l - m1, name, l - m2, name, q, name, l + m1, name, l + m2))
+        for si, m in enumerate(d.singles):
+            o.append("        u%s.slo[%d] = %s%d; u%s.shi[%d] = %s%d;" % (name, si, name, l - m, name, si, name, l + m))
+        o.append("        u%s.ctr = %s%d;" % (name, name, l))
+    if n == 1:
+        o.append("        (void)s;")
+    o.append("    }")
     o.append("};")
     return "\n".join(o), n_f2, n_f1
 

@@ -15,7 +15,7 @@ torch.manual_seed(0)
 dev = "cuda"
 t0 = time.time()
 launches = 0
-sizes = [16, 17, 32, 16 * 147, 16 * 148, 16 * 149 + 1, 16 * 148 * 2, 16 * 148 * 3 + 5, 16 * 148 * 4, 16 * 148 * 5 - 16, 16 * 1000 + 7,
+sizes = [2, 12, 13, 16, 17, 32, 12 * 147, 12 * 148, 12 * 149 + 1, 12 * 148 * 2, 12 * 148 * 5 + 5, 12 * 148 * 6, 12 * 148 * 7 - 12, 16 * 1000 + 7,
          1 << 16, (1 << 17) + 48, 1 << 18]
 for L in (8, 6):
     M = (L + 1) ** 2
