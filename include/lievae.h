@@ -142,6 +142,26 @@ int lv_so3_reparam_eazyz_bwd_f64(const double* mu, const double* sigma, const do
                                  const double* gangles, const double* glq, double* gmu, double* gsigma, int64_t n, int64_t B,
                                  int k, void* stream);
 
+/* ---- the same kernels with IN-KERNEL noise (SURVEY.md section 7 "Noise"): eps ~ N(0,1) is not an input but generated per
+ *   sample by Philox4x32-10 (key = seed, counter = offset + flat sample index over (n,B); Box-Muller), so the reference's
+ *   `Normal(0,1).sample((n,))` (reparameterize.py:137-141) never exists in memory; the backward regenerates the same
+ *   numbers from (seed, offset).  angles == NULL: plain reparameterize (z required); angles != NULL: fused with
+ *   group_matrix_to_eazyz (z optional).  Backward: gangles selects the fused variant the same way.
+ *   lv_philox_normal_*: out (rows,3) = exactly the eps these kernels use for samples offset .. offset + rows - 1
+ *   (tests; callers that want the noise itself).  The explicit-eps entry points above stay the parity path. ---- */
+int lv_so3_reparam_philox_fwd_f32(const float* mu, const float* sigma, int64_t seed, int64_t offset, float* z, float* angles,
+                                  float* log_q, int64_t n, int64_t B, int k, void* stream);
+int lv_so3_reparam_philox_bwd_f32(const float* mu, const float* sigma, int64_t seed, int64_t offset, const float* gz,
+                                  const float* gangles, const float* glq, float* gmu, float* gsigma, int64_t n, int64_t B,
+                                  int k, void* stream);
+int lv_so3_reparam_philox_fwd_f64(const double* mu, const double* sigma, int64_t seed, int64_t offset, double* z, double* angles,
+                                  double* log_q, int64_t n, int64_t B, int k, void* stream);
+int lv_so3_reparam_philox_bwd_f64(const double* mu, const double* sigma, int64_t seed, int64_t offset, const double* gz,
+                                  const double* gangles, const double* glq, double* gmu, double* gsigma, int64_t n, int64_t B,
+                                  int k, void* stream);
+int lv_philox_normal_f32(float* out, int64_t rows, int64_t seed, int64_t offset, void* stream);
+int lv_philox_normal_f64(double* out, int64_t rows, int64_t seed, int64_t offset, void* stream);
+
 /* ---- encoder heads fused into the reparameterize kernels: from encoder features h (B,Din), Din <= 32,
  *   mu    = mean_map(Wm h + bm)                mode 0: rodrigues (AlgebraMean reparameterize.py:148-155, Dm = 3)
  *                                              mode 1: quaternions_to_group_matrix (QuaternionMean :158-164, Dm = 4)
@@ -152,15 +172,17 @@ int lv_so3_reparam_eazyz_bwd_f64(const double* mu, const double* sigma, const do
  *   mu (B,9) / sigma (B,3) are optional outputs (module attributes); give `angles` for the Euler-fused variant (z optional).
  *   Backward: gh (n,B,Din) per sample (reduce over n with lv_sum_leading_f32), gWb ((Dm+3), Din+1): rows of the mean head
  *   then of the sigma head, each = the gradient of its weight row followed by its bias gradient, summed over all samples through `workspace`
- *   (lv_so3_head_reparam_bwd_workspace_floats floats; deterministic two-pass reduction). ---- */
+ *   (lv_so3_head_reparam_bwd_workspace_floats floats; deterministic two-pass reduction).  gmu (B,9) / gsigma (B,3), each optional:
+ *   gradients that reach the mu / sigma OUTPUTS from outside the sampler (SO3reparameterize.kl(), regularisers on mu_lie or
+ *   sigma); they are added to the sampler's own gradient before the mean map / softplus are pulled back. ---- */
 int64_t lv_so3_head_reparam_bwd_workspace_floats(int64_t n, int64_t B, int Din, int mode);
 int lv_so3_head_reparam_fwd_f32(const float* h, const float* Wm, const float* bm, const float* Ws, const float* bs,
                                 const float* eps, float* mu, float* sigma, float* z, float* angles, float* log_q, int64_t n,
                                 int64_t B, int Din, int mode, int k, void* stream);
 int lv_so3_head_reparam_bwd_f32(const float* h, const float* Wm, const float* bm, const float* Ws, const float* bs,
-                                const float* eps, const float* gz, const float* gangles, const float* glq, float* gh, float* gWb,
-                                float* workspace, int64_t workspace_floats, int64_t n, int64_t B, int Din, int mode, int k,
-                                void* stream);
+                                const float* eps, const float* gz, const float* gangles, const float* glq, const float* gmu,
+                                const float* gsigma, float* gh, float* gWb, float* workspace, int64_t workspace_floats, int64_t n,
+                                int64_t B, int Din, int mode, int k, void* stream);
 
 /* ---- block-diagonal Wigner-D action on a spectrum, degrees lmin..lmax (<= 8), C channels.
  *   block_wigner_matrix_multiply lie_tools.py:226-253, wigner_d_matrix lie_tools.py:211-223,
@@ -178,23 +200,6 @@ int lv_wigner_apply_fwd_f32(const float* angles, const float* spectrum, float* o
 int lv_wigner_apply_bwd_f32(const float* angles, const float* spectrum, const float* gout, float* gangles,
                             float* gspectrum, float* workspace, int64_t workspace_floats, int64_t N, int lmin,
                             int lmax, int C, int shared_spectrum, int transpose, void* stream);
-
-/* ---- the same action for ANY degree range (lmax <= lv_wigner_generic_max_degree()) and for float64: run-time loops over
- *   a caller-owned dense J table `jtable` = J_0 | J_1 | ... | J_lmax (row-major (2l+1)^2 blocks, block l at offset
- *   l(2l-1)(2l+1)/3; lie_tools.j_matrix lie_tools.py:10-14).  Covers what the unrolled kernels above do not
- *   (degrees > 8, FP64).  Backward writes PER-COLUMN results: gangle_parts (N,C,3) -- sum over C for g_angles -- and
- *   gspectrum (N,M,C) -- sum over N for a shared spectrum; the caller reduces (deterministic, no atomics). ---- */
-int lv_wigner_generic_max_degree(void);
-int lv_wigner_generic_fwd_f32(const float* angles, const float* spectrum, const float* jtable, float* out, int64_t N,
-                              int lmin, int lmax, int C, int shared_spectrum, int transpose, void* stream);
-int lv_wigner_generic_bwd_f32(const float* angles, const float* spectrum, const float* jtable, const float* gout,
-                              float* gangle_parts, float* gspectrum, int64_t N, int lmin, int lmax, int C,
-                              int shared_spectrum, int transpose, void* stream);
-int lv_wigner_generic_fwd_f64(const double* angles, const double* spectrum, const double* jtable, double* out, int64_t N,
-                              int lmin, int lmax, int C, int shared_spectrum, int transpose, void* stream);
-int lv_wigner_generic_bwd_f64(const double* angles, const double* spectrum, const double* jtable, const double* gout,
-                              double* gangle_parts, double* gspectrum, int64_t N, int lmin, int lmax, int C,
-                              int shared_spectrum, int transpose, void* stream);
 
 /* ---- the same action for ANY degree range (lmax <= lv_wigner_generic_max_degree()) and for float64: run-time loops over
  *   a caller-owned dense J table `jtable` = J_0 | J_1 | ... | J_lmax (row-major (2l+1)^2 blocks, block l at offset

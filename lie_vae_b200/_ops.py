@@ -212,6 +212,7 @@ class SO3Reparam(Function):
                        _cabi.ptr(log_q), n, B, int(k), _stream())
         ctx.save_for_backward(mu_c, sg_c, ep_c)
         ctx.k = int(k)
+        ctx.set_materialize_grads(False)       # unused outputs arrive as None, not as zero tensors
         return z, log_q
 
     @staticmethod
@@ -260,6 +261,7 @@ class SO3ReparamEazyz(Function):
                        _cabi.ptr(angles), _cabi.ptr(log_q), n, B, int(k), _stream())
         ctx.save_for_backward(mu_c, sg_c, ep_c)
         ctx.k = int(k)
+        ctx.set_materialize_grads(False)       # unused outputs arrive as None, not as zero tensors
         return angles, log_q
 
     @staticmethod
@@ -278,6 +280,65 @@ class SO3ReparamEazyz(Function):
         return sum_leading(gmu), sum_leading(gsg), None, None
 
 
+class SO3ReparamPhilox(Function):
+    """(mu (B,3,3), sigma (B,3), n, k, seed, offset, euler) -> (pose, log_q) with IN-KERNEL noise.
+
+    eps ~ N(0,1) of the reference (``reparameterize.py:137-141``) is generated inside the kernel by Philox4x32-10
+    keyed by ``seed`` at counter ``offset + flat sample index`` and regenerated by the backward: it is never stored.
+    ``pose`` is z (n,B,3,3), or its ZYZ Euler angles (n,B,3) with ``euler``.  ``philox_normal`` returns the same eps.
+    """
+
+    @staticmethod
+    def forward(ctx, mu, sigma, n, k, seed, offset, euler):
+        dev = _require_cuda(mu, sigma)
+        sfx = _sfx(mu)
+        if sigma.dtype != mu.dtype:
+            raise TypeError("so3_reparameterize: mu, sigma must share a dtype, got %s / %s" % (mu.dtype, sigma.dtype))
+        if mu.dim() != 3 or tuple(mu.shape[1:]) != (3, 3):
+            raise ValueError("mu must be (B,3,3), got %s" % (tuple(mu.shape),))
+        B = mu.shape[0]
+        if tuple(sigma.shape) != (B, 3):
+            raise ValueError("sigma must be (B,3), got %s" % (tuple(sigma.shape),))
+        n = int(n)
+        mu_c, sg_c = mu.contiguous(), sigma.contiguous()
+        pose = torch.empty((n, B, 3) if euler else (n, B, 3, 3), dtype=mu.dtype, device=dev)
+        log_q = torch.empty((n, B), dtype=mu.dtype, device=dev)
+        with _on(dev):
+            _cabi.call("lv_so3_reparam_philox_fwd_" + sfx, _cabi.ptr(mu_c), _cabi.ptr(sg_c), int(seed), int(offset),
+                       None if euler else _cabi.ptr(pose), _cabi.ptr(pose) if euler else None, _cabi.ptr(log_q), n, B, int(k), _stream())
+        ctx.save_for_backward(mu_c, sg_c)
+        ctx.meta = (n, int(k), int(seed), int(offset), bool(euler))
+        ctx.set_materialize_grads(False)       # unused outputs arrive as None, not as zero tensors
+        return pose, log_q
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gpose, glq):
+        mu, sigma = ctx.saved_tensors
+        n, k, seed, offset, euler = ctx.meta
+        B, dev = mu.shape[0], mu.device
+        if euler and gpose is None:
+            gpose = torch.zeros((n, B, 3), dtype=mu.dtype, device=dev)
+        gpose = None if gpose is None else gpose.contiguous()
+        glq = None if glq is None else glq.contiguous()
+        gmu = torch.empty((n, B, 3, 3), dtype=mu.dtype, device=dev)
+        gsg = torch.empty((n, B, 3), dtype=mu.dtype, device=dev)
+        with _on(dev):
+            _cabi.call("lv_so3_reparam_philox_bwd_" + _sfx(mu), _cabi.ptr(mu), _cabi.ptr(sigma), seed, offset,
+                       None if euler else _cabi.ptr(gpose), _cabi.ptr(gpose) if euler else None, _cabi.ptr(glq),
+                       _cabi.ptr(gmu), _cabi.ptr(gsg), n, B, k, _stream())
+        return sum_leading(gmu), sum_leading(gsg), None, None, None, None, None
+
+
+def philox_normal(rows, seed, offset=0, dtype=torch.float32, device="cuda"):
+    """(rows, 3) standard normals: exactly the eps SO3ReparamPhilox uses for flat samples offset .. offset + rows - 1."""
+    out = torch.empty((int(rows), 3), dtype=dtype, device=device)
+    dev = _require_cuda(out)
+    with _on(dev):
+        _cabi.call("lv_philox_normal_" + _sfx(out), _cabi.ptr(out), int(rows), int(seed), int(offset), _stream())
+    return out
+
+
 HEAD_MODES = {"alg": 0, "q": 1, "s2s2": 2, "s2s1": 3}      # mean maps the fused head kernels know (mean-head rows: 3, 4, 6, 5)
 HEAD_MAX_DIN = 32
 
@@ -287,7 +348,8 @@ class SO3HeadReparam(Function):
 
     Encoder heads fused into the reparameterize kernel: mu = mean_map(Wm h + bm), sigma = softplus(Ws h + bs), then the
     sampler.  ``pose`` is z (n,B,3,3), or its ZYZ Euler angles (n,B,3) with ``euler``.  mu (B,3,3) and sigma (B,3)
-    are returned for the modules' attributes and are not differentiable outputs.   float32.
+    (the modules' ``mu_lie`` / ``sigma`` attributes) are differentiable outputs like the other two: gradients that reach
+    them from outside the sampler are folded into the same backward kernel.   float32.
     """
 
     @staticmethod
@@ -318,20 +380,22 @@ class SO3HeadReparam(Function):
                        n, B, Din, m, int(k), _stream())
         ctx.save_for_backward(*saved)
         ctx.meta = (m, int(k), bool(euler), dm)
-        ctx.mark_non_differentiable(mu, sigma)
+        ctx.set_materialize_grads(False)       # unused outputs arrive as None, not as zero tensors
         return pose, log_q, mu, sigma
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, gpose, glq, _gmu, _gsigma):
+    def backward(ctx, gpose, glq, gmu, gsigma):
         saved = ctx.saved_tensors
         h, eps = saved[0], saved[5]
         m, k, euler, dm = ctx.meta
         n, B, Din = eps.shape[0], h.shape[0], h.shape[1]
         dev = h.device
         f32 = dict(dtype=torch.float32, device=dev)
-        if gpose is None and glq is None:
+        if gpose is None and glq is None and gmu is None and gsigma is None:
             return tuple(torch.zeros_like(t) for t in saved[:5]) + (None, None, None, None)
+        gmu = None if gmu is None else gmu.contiguous()
+        gsigma = None if gsigma is None else gsigma.contiguous()
         if euler and gpose is None:
             gpose = torch.zeros((n, B, 3), **f32)
         gpose = None if gpose is None else gpose.contiguous()
@@ -342,8 +406,8 @@ class SO3HeadReparam(Function):
             nws = _cabi.lib().lv_so3_head_reparam_bwd_workspace_floats(n, B, Din, m)
             ws = torch.empty(max(nws, 1), **f32)
             _cabi.call("lv_so3_head_reparam_bwd_f32", *[_cabi.ptr(t) for t in saved],
-                       None if euler else _cabi.ptr(gpose), _cabi.ptr(gpose) if euler else None, _cabi.ptr(glq), _cabi.ptr(gh),
-                       _cabi.ptr(gwb), _cabi.ptr(ws), nws, n, B, Din, m, k, _stream())
+                       None if euler else _cabi.ptr(gpose), _cabi.ptr(gpose) if euler else None, _cabi.ptr(glq),
+                       _cabi.ptr(gmu), _cabi.ptr(gsigma), _cabi.ptr(gh), _cabi.ptr(gwb), _cabi.ptr(ws), nws, n, B, Din, m, k, _stream())
         return sum_leading(gh), gwb[:dm, :Din], gwb[:dm, Din], gwb[dm:, :Din], gwb[dm:, Din], None, None, None, None
 
 

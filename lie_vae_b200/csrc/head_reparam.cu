@@ -175,8 +175,8 @@ __global__ void __launch_bounds__(HR_TILE)
 head_reparam_bwd_kernel(const float* __restrict__ h, const float* __restrict__ Wm, const float* __restrict__ bm, const float* __restrict__ Ws,
                         const float* __restrict__ bs,
                         const float* __restrict__ eps, const float* __restrict__ gz, const float* __restrict__ gangles,
-                        const float* __restrict__ glq, float* __restrict__ gh, float* __restrict__ partial, int64_t total,
-                        int64_t B, int Din, int krt) {
+                        const float* __restrict__ glq, const float* __restrict__ gmu_ext, const float* __restrict__ gsg_ext,
+                        float* __restrict__ gh, float* __restrict__ partial, int64_t total, int64_t B, int Din, int krt) {
     constexpr int DM = hr_mean_rows(MODE), DT = DM + 3;
     extern __shared__ __align__(16) float smem[];
     float* s_w = smem;                                        // [(Din+1)][12]
@@ -213,6 +213,18 @@ head_reparam_bwd_kernel(const float* __restrict__ h, const float* __restrict__ W
         }
         const float gl = glq != nullptr ? glq[i0 + t] : 0.f;
         reparam_sample_bwd<float, KT, EULER>(m, sg, ep, G, ge, gl, glq != nullptr, krt, gm, gsg);
+        // gradients that reach mu (B,3,3) / sigma (B,3) from outside the sampler (the modules expose them as mu_lie / sigma:
+        // kl(), regularisers): mu and sigma are broadcast over n, so each is added once, in the datapoint's first sample
+        if (i0 + t < B) {
+            if (gmu_ext != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 9; ++j) gm[j] += __ldg(gmu_ext + (i0 + t) * 9 + j);
+            }
+            if (gsg_ext != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) gsg[j] += __ldg(gsg_ext + (i0 + t) * 3 + j);
+            }
+        }
         hr_mean_bwd<MODE>(pre, gm, gpre);
 #pragma unroll
         for (int j = 0; j < 3; ++j) gpre[DM + j] = gsg[j] * hr_softplus_grad(pre[DM + j]);
@@ -288,22 +300,24 @@ static int hr_launch_fwd(const float* h, const float* Wm, const float* bm, const
 }
 template <int MODE, bool EULER, int KT>
 static int hr_launch_bwd_k(const float* h, const float* Wm, const float* bm, const float* Ws, const float* bs, const float* eps, const float* gz, const float* gangles,
-                           const float* glq, float* gh, float* partial, int64_t total, int64_t B, int Din, int k, cudaStream_t st) {
+                           const float* glq, const float* gmu_ext, const float* gsg_ext, float* gh, float* partial, int64_t total, int64_t B, int Din, int k,
+                           cudaStream_t st) {
     const unsigned grid = unsigned((total + HR_TILE - 1) / HR_TILE);
     const size_t smem = size_t((Din + 1) * HR_WPAD + HR_TILE * (3 + 9 + 3 + HR_WPAD + 2 * Din)) * 4;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(head_reparam_bwd_kernel<MODE, KT, EULER>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
         if (e != cudaSuccess) { set_error("so3_head_reparam_bwd: cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e)); return int(e); }
     }
-    head_reparam_bwd_kernel<MODE, KT, EULER><<<grid, HR_TILE, smem, st>>>(h, Wm, bm, Ws, bs, eps, gz, gangles, glq, gh, partial, total, B, Din, k);
+    head_reparam_bwd_kernel<MODE, KT, EULER><<<grid, HR_TILE, smem, st>>>(h, Wm, bm, Ws, bs, eps, gz, gangles, glq, gmu_ext, gsg_ext, gh, partial, total, B, Din, k);
     return check_launch("so3_head_reparam_bwd");
 }
 template <int MODE, bool EULER>
 static int hr_launch_bwd(const float* h, const float* Wm, const float* bm, const float* Ws, const float* bs, const float* eps, const float* gz, const float* gangles,
-                         const float* glq, float* gh, float* partial, int64_t total, int64_t B, int Din, int k, cudaStream_t st) {
-    if (k == 3) return hr_launch_bwd_k<MODE, EULER, 3>(h, Wm, bm, Ws, bs, eps, gz, gangles, glq, gh, partial, total, B, Din, k, st);
-    if (k == 10) return hr_launch_bwd_k<MODE, EULER, 10>(h, Wm, bm, Ws, bs, eps, gz, gangles, glq, gh, partial, total, B, Din, k, st);
-    return hr_launch_bwd_k<MODE, EULER, 0>(h, Wm, bm, Ws, bs, eps, gz, gangles, glq, gh, partial, total, B, Din, k, st);
+                         const float* glq, const float* gmu_ext, const float* gsg_ext, float* gh, float* partial, int64_t total, int64_t B, int Din, int k,
+                         cudaStream_t st) {
+    if (k == 3) return hr_launch_bwd_k<MODE, EULER, 3>(h, Wm, bm, Ws, bs, eps, gz, gangles, glq, gmu_ext, gsg_ext, gh, partial, total, B, Din, k, st);
+    if (k == 10) return hr_launch_bwd_k<MODE, EULER, 10>(h, Wm, bm, Ws, bs, eps, gz, gangles, glq, gmu_ext, gsg_ext, gh, partial, total, B, Din, k, st);
+    return hr_launch_bwd_k<MODE, EULER, 0>(h, Wm, bm, Ws, bs, eps, gz, gangles, glq, gmu_ext, gsg_ext, gh, partial, total, B, Din, k, st);
 }
 
 }  // namespace lv
@@ -333,8 +347,8 @@ extern "C" int lv_so3_head_reparam_fwd_f32(const float* h, const float* Wm, cons
 }
 
 extern "C" int lv_so3_head_reparam_bwd_f32(const float* h, const float* Wm, const float* bm, const float* Ws, const float* bs, const float* eps, const float* gz,
-                                           const float* gangles, const float* glq, float* gh, float* gWb, float* workspace,
-                                           int64_t workspace_floats, int64_t n, int64_t B, int Din, int mode, int k, void* stream) {
+                                           const float* gangles, const float* glq, const float* gmu, const float* gsigma, float* gh, float* gWb,
+                                           float* workspace, int64_t workspace_floats, int64_t n, int64_t B, int Din, int mode, int k, void* stream) {
     int rc = lv::hr_check("so3_head_reparam_bwd", n, B, Din, mode, k);
     if (rc) return rc;
     const int64_t total = n * B;
@@ -346,10 +360,10 @@ extern "C" int lv_so3_head_reparam_bwd_f32(const float* h, const float* Wm, cons
         if (e != cudaSuccess) { lv::set_error("so3_head_reparam_bwd: memset: %s", cudaGetErrorString(e)); return int(e); }
         return LV_OK;
     }
-    if (!h || !Wm || !bm || !Ws || !bs || !eps || !gh || (!gz && !gangles && !glq)) { lv::set_error("so3_head_reparam_bwd: null pointer"); return LV_ERR_ARG; }
+    if (!h || !Wm || !bm || !Ws || !bs || !eps || !gh || (!gz && !gangles && !glq && !gmu && !gsigma)) { lv::set_error("so3_head_reparam_bwd: null pointer"); return LV_ERR_ARG; }
     const int64_t need = lv_so3_head_reparam_bwd_workspace_floats(n, B, Din, mode);
     if (!workspace || workspace_floats < need) { lv::set_error("so3_head_reparam_bwd: workspace of %lld floats required", (long long)need); return LV_ERR_ARG; }
-    rc = HR_DISPATCH(mode, gangles != nullptr, hr_launch_bwd, h, Wm, bm, Ws, bs, eps, gz, gangles, glq, gh, workspace, total, B, Din, k, st);
+    rc = HR_DISPATCH(mode, gangles != nullptr, hr_launch_bwd, h, Wm, bm, Ws, bs, eps, gz, gangles, glq, gmu, gsigma, gh, workspace, total, B, Din, k, st);
     if (rc) return rc;
     const int64_t nblk = (total + lv::HR_TILE - 1) / lv::HR_TILE;
     lv::head_reduce_partials<<<(NO + 31) / 32, dim3(32, 8), 0, st>>>(workspace, gWb, nblk, NO);

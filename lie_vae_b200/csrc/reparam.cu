@@ -63,7 +63,7 @@ template <typename T, int KT, bool EULER, int TILE>
 __global__ void __launch_bounds__(TILE)
 so3_reparam_fwd_kernel(const T* __restrict__ mu, const T* __restrict__ sigma, const T* __restrict__ eps,
                        T* __restrict__ z, T* __restrict__ angles, T* __restrict__ log_q, int64_t total,
-                       int64_t B, int krt, int aligned16) {
+                       int64_t B, int krt, int aligned16, uint64_t seed, uint64_t offset) {
     __shared__ __align__(16) T s_m[TILE * 9];   // mu in, z out (same row, same thread)
     __shared__ __align__(16) T s_s[TILE * 3];
     __shared__ __align__(16) T s_e[TILE * 3];   // eps in, Euler angles out
@@ -77,18 +77,20 @@ so3_reparam_fwd_kernel(const T* __restrict__ mu, const T* __restrict__ sigma, co
         if (threadIdx.x == 0) {
             mbar_init(&s_bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            mbar_expect_tx(&s_bar, uint32_t(TILE * 15 * sizeof(T)));
+            mbar_expect_tx(&s_bar, uint32_t(TILE * (eps != nullptr ? 15 : 12) * sizeof(T)));
             tma_load(s_m, mu + b0 * 9, uint32_t(TILE * 9 * sizeof(T)), &s_bar);
             tma_load(s_s, sigma + b0 * 3, uint32_t(TILE * 3 * sizeof(T)), &s_bar);
-            tma_load(s_e, eps + i0 * 3, uint32_t(TILE * 3 * sizeof(T)), &s_bar);
+            if (eps != nullptr) tma_load(s_e, eps + i0 * 3, uint32_t(TILE * 3 * sizeof(T)), &s_bar);
         }
         __syncthreads();                  // the barrier word is initialised before anyone polls it
         mbar_wait(&s_bar, 0);
     } else {
         stage_bcast<T, 9, TILE>(s_m, mu, i0, rows, B);
         stage_bcast<T, 3, TILE>(s_s, sigma, i0, rows, B);
-        if (full) tile_g2s_full<T, TILE * 3, TILE>(s_e, eps + i0 * 3);
-        else tile_g2s(s_e, eps + i0 * 3, rows * 3);
+        if (eps != nullptr) {
+            if (full) tile_g2s_full<T, TILE * 3, TILE>(s_e, eps + i0 * 3);
+            else tile_g2s(s_e, eps + i0 * 3, rows * 3);
+        }
         tile_async_wait();
         __syncthreads();
     }
@@ -98,7 +100,13 @@ so3_reparam_fwd_kernel(const T* __restrict__ mu, const T* __restrict__ sigma, co
 #pragma unroll
         for (int j = 0; j < 9; ++j) m[j] = s_m[t * 9 + j];
 #pragma unroll
-        for (int j = 0; j < 3; ++j) { sg[j] = s_s[t * 3 + j]; ep[j] = s_e[t * 3 + j]; }
+        for (int j = 0; j < 3; ++j) sg[j] = s_s[t * 3 + j];
+        if (eps != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) ep[j] = s_e[t * 3 + j];
+        } else {
+            philox_normal3<T>(seed, offset + uint64_t(i0 + t), ep);
+        }
         reparam_sample_fwd<T, KT, EULER>(m, sg, ep, krt, log_q != nullptr, zr, e, &lq);
 #pragma unroll
         for (int j = 0; j < 9; ++j) s_m[t * 9 + j] = zr[j];
@@ -136,7 +144,8 @@ template <typename T, int KT, bool EULER, int TILE>
 __global__ void __launch_bounds__(TILE)
 so3_reparam_bwd_kernel(const T* __restrict__ mu, const T* __restrict__ sigma, const T* __restrict__ eps,
                        const T* __restrict__ gz, const T* __restrict__ gangles, const T* __restrict__ glq,
-                       T* __restrict__ gmu, T* __restrict__ gsigma, int64_t total, int64_t B, int krt, int aligned16) {
+                       T* __restrict__ gmu, T* __restrict__ gsigma, int64_t total, int64_t B, int krt, int aligned16,
+                       uint64_t seed, uint64_t offset) {
     __shared__ __align__(16) T s_m[TILE * 9];
     __shared__ __align__(16) T s_g[TILE * 9];   // gz in, g_mu out
     __shared__ __align__(16) T s_s[TILE * 3];
@@ -152,10 +161,10 @@ so3_reparam_bwd_kernel(const T* __restrict__ mu, const T* __restrict__ sigma, co
         if (threadIdx.x == 0) {
             mbar_init(&s_bar, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            mbar_expect_tx(&s_bar, uint32_t(TILE * (15 + (gz != nullptr ? 9 : 0) + (EULER ? 3 : 0)) * sizeof(T)));
+            mbar_expect_tx(&s_bar, uint32_t(TILE * (12 + (eps != nullptr ? 3 : 0) + (gz != nullptr ? 9 : 0) + (EULER ? 3 : 0)) * sizeof(T)));
             tma_load(s_m, mu + b0 * 9, uint32_t(TILE * 9 * sizeof(T)), &s_bar);
             tma_load(s_s, sigma + b0 * 3, uint32_t(TILE * 3 * sizeof(T)), &s_bar);
-            tma_load(s_e, eps + i0 * 3, uint32_t(TILE * 3 * sizeof(T)), &s_bar);
+            if (eps != nullptr) tma_load(s_e, eps + i0 * 3, uint32_t(TILE * 3 * sizeof(T)), &s_bar);
             if (gz != nullptr) tma_load(s_g, gz + i0 * 9, uint32_t(TILE * 9 * sizeof(T)), &s_bar);
             if (EULER) tma_load(s_a, gangles + i0 * 3, uint32_t(TILE * 3 * sizeof(T)), &s_bar);
         }
@@ -165,11 +174,11 @@ so3_reparam_bwd_kernel(const T* __restrict__ mu, const T* __restrict__ sigma, co
         stage_bcast<T, 9, TILE>(s_m, mu, i0, rows, B);
         stage_bcast<T, 3, TILE>(s_s, sigma, i0, rows, B);
         if (full) {
-            tile_g2s_full<T, TILE * 3, TILE>(s_e, eps + i0 * 3);
+            if (eps != nullptr) tile_g2s_full<T, TILE * 3, TILE>(s_e, eps + i0 * 3);
             if (gz != nullptr) tile_g2s_full<T, TILE * 9, TILE>(s_g, gz + i0 * 9);
             if (EULER) tile_g2s_full<T, TILE * 3, TILE>(s_a, gangles + i0 * 3);
         } else {
-            tile_g2s(s_e, eps + i0 * 3, rows * 3);
+            if (eps != nullptr) tile_g2s(s_e, eps + i0 * 3, rows * 3);
             if (gz != nullptr) tile_g2s(s_g, gz + i0 * 9, rows * 9);
             if (EULER) tile_g2s(s_a, gangles + i0 * 3, rows * 3);
         }
@@ -182,7 +191,13 @@ so3_reparam_bwd_kernel(const T* __restrict__ mu, const T* __restrict__ sigma, co
 #pragma unroll
         for (int j = 0; j < 9; ++j) { m[j] = s_m[t * 9 + j]; G[j] = gz != nullptr ? s_g[t * 9 + j] : T(0); }
 #pragma unroll
-        for (int j = 0; j < 3; ++j) { sg[j] = s_s[t * 3 + j]; ep[j] = s_e[t * 3 + j]; }
+        for (int j = 0; j < 3; ++j) sg[j] = s_s[t * 3 + j];
+        if (eps != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) ep[j] = s_e[t * 3 + j];
+        } else {
+            philox_normal3<T>(seed, offset + uint64_t(i0 + t), ep);
+        }
         if (EULER) {
 #pragma unroll
             for (int j = 0; j < 3; ++j) ge[j] = s_a[t * 3 + j];
@@ -246,7 +261,7 @@ template <typename T, int KT, bool EULER, int TILE, int NS>
 __global__ void __launch_bounds__(TILE)
 so3_reparam_fwd_pipe_kernel(const T* __restrict__ mu, const T* __restrict__ sigma, const T* __restrict__ eps,
                             T* __restrict__ z, T* __restrict__ angles, T* __restrict__ log_q, int64_t ntiles,
-                            int64_t B, int krt) {
+                            int64_t B, int krt, uint64_t seed, uint64_t offset) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Stage = RpFwdStage<T, TILE, EULER>;
     Stage* st = reinterpret_cast<Stage*>(smem_raw);
@@ -254,10 +269,10 @@ so3_reparam_fwd_pipe_kernel(const T* __restrict__ mu, const T* __restrict__ sigm
     const int t = threadIdx.x;
     auto load = [&](int64_t tile, int s) {
         const int64_t i0 = tile * TILE, b0 = i0 < B ? i0 : i0 % B;
-        mbar_expect_tx(&s_full[s], uint32_t(TILE * 15 * sizeof(T)));
+        mbar_expect_tx(&s_full[s], uint32_t(TILE * (eps != nullptr ? 15 : 12) * sizeof(T)));
         tma_load(st[s].m, mu + b0 * 9, uint32_t(TILE * 9 * sizeof(T)), &s_full[s]);
         tma_load(st[s].s, sigma + b0 * 3, uint32_t(TILE * 3 * sizeof(T)), &s_full[s]);
-        tma_load(st[s].e, eps + i0 * 3, uint32_t(TILE * 3 * sizeof(T)), &s_full[s]);
+        if (eps != nullptr) tma_load(st[s].e, eps + i0 * 3, uint32_t(TILE * 3 * sizeof(T)), &s_full[s]);
     };
     if (t == 0) {
 #pragma unroll
@@ -279,7 +294,13 @@ so3_reparam_fwd_pipe_kernel(const T* __restrict__ mu, const T* __restrict__ sigm
 #pragma unroll
         for (int j = 0; j < 9; ++j) m[j] = st[s].m[t * 9 + j];
 #pragma unroll
-        for (int j = 0; j < 3; ++j) { sg[j] = st[s].s[t * 3 + j]; ep[j] = st[s].e[t * 3 + j]; }
+        for (int j = 0; j < 3; ++j) sg[j] = st[s].s[t * 3 + j];
+        if (eps != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) ep[j] = st[s].e[t * 3 + j];
+        } else {
+            philox_normal3<T>(seed, offset + uint64_t(i0 + t), ep);
+        }
         reparam_sample_fwd<T, KT, EULER>(m, sg, ep, krt, log_q != nullptr, zr, e, &lq);
 #pragma unroll
         for (int j = 0; j < 9; ++j) st[s].m[t * 9 + j] = zr[j];
@@ -303,7 +324,8 @@ template <typename T, int KT, bool EULER, int TILE, int NS>
 __global__ void __launch_bounds__(TILE)
 so3_reparam_bwd_pipe_kernel(const T* __restrict__ mu, const T* __restrict__ sigma, const T* __restrict__ eps,
                             const T* __restrict__ gz, const T* __restrict__ gangles, const T* __restrict__ glq,
-                            T* __restrict__ gmu, T* __restrict__ gsigma, int64_t ntiles, int64_t B, int krt) {
+                            T* __restrict__ gmu, T* __restrict__ gsigma, int64_t ntiles, int64_t B, int krt,
+                            uint64_t seed, uint64_t offset) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Stage = RpBwdStage<T, TILE, EULER>;
     Stage* st = reinterpret_cast<Stage*>(smem_raw);
@@ -311,10 +333,10 @@ so3_reparam_bwd_pipe_kernel(const T* __restrict__ mu, const T* __restrict__ sigm
     const int t = threadIdx.x;
     auto load = [&](int64_t tile, int s) {
         const int64_t i0 = tile * TILE, b0 = i0 < B ? i0 : i0 % B;
-        mbar_expect_tx(&s_full[s], uint32_t(TILE * (15 + (gz != nullptr ? 9 : 0) + (EULER ? 3 : 0)) * sizeof(T)));
+        mbar_expect_tx(&s_full[s], uint32_t(TILE * (12 + (eps != nullptr ? 3 : 0) + (gz != nullptr ? 9 : 0) + (EULER ? 3 : 0)) * sizeof(T)));
         tma_load(st[s].m, mu + b0 * 9, uint32_t(TILE * 9 * sizeof(T)), &s_full[s]);
         tma_load(st[s].s, sigma + b0 * 3, uint32_t(TILE * 3 * sizeof(T)), &s_full[s]);
-        tma_load(st[s].e, eps + i0 * 3, uint32_t(TILE * 3 * sizeof(T)), &s_full[s]);
+        if (eps != nullptr) tma_load(st[s].e, eps + i0 * 3, uint32_t(TILE * 3 * sizeof(T)), &s_full[s]);
         if (gz != nullptr) tma_load(st[s].g, gz + i0 * 9, uint32_t(TILE * 9 * sizeof(T)), &s_full[s]);
         if (EULER) tma_load(st[s].a, gangles + i0 * 3, uint32_t(TILE * 3 * sizeof(T)), &s_full[s]);
     };
@@ -339,7 +361,13 @@ so3_reparam_bwd_pipe_kernel(const T* __restrict__ mu, const T* __restrict__ sigm
 #pragma unroll
         for (int j = 0; j < 9; ++j) { m[j] = st[s].m[t * 9 + j]; G[j] = gz != nullptr ? st[s].g[t * 9 + j] : T(0); }
 #pragma unroll
-        for (int j = 0; j < 3; ++j) { sg[j] = st[s].s[t * 3 + j]; ep[j] = st[s].e[t * 3 + j]; }
+        for (int j = 0; j < 3; ++j) sg[j] = st[s].s[t * 3 + j];
+        if (eps != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) ep[j] = st[s].e[t * 3 + j];
+        } else {
+            philox_normal3<T>(seed, offset + uint64_t(i0 + t), ep);
+        }
         if (EULER) {
 #pragma unroll
             for (int j = 0; j < 3; ++j) ge[j] = st[s].a[t * 3 + j];
@@ -358,6 +386,17 @@ so3_reparam_bwd_pipe_kernel(const T* __restrict__ mu, const T* __restrict__ sigm
         }
     }
     if (t == 0) tma_store_wait_read<0>();      // the staging buffers stay valid until the copy engine has read them
+}
+
+// eps (rows, 3) of the Philox stream the fused kernels draw from when they are given no eps: row i = sample offset + i
+template <typename T>
+__global__ void __launch_bounds__(256)
+philox_normal_kernel(T* __restrict__ out, int64_t rows, uint64_t seed, uint64_t offset) {
+    const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
+    if (i >= rows) return;
+    T ep[3];
+    philox_normal3<T>(seed, offset + uint64_t(i), ep);
+    out[i * 3] = ep[0]; out[i * 3 + 1] = ep[1]; out[i * 3 + 2] = ep[2];
 }
 
 }  // namespace lv
@@ -403,7 +442,7 @@ static int pipe_grid(K kernel, int threads, size_t smem, int64_t ntiles, int* ca
 
 template <typename T, int KT, bool EULER, int TILE>
 static int reparam_fwd_launch(const T* mu, const T* sigma, const T* eps, T* z, T* angles, T* log_q, int64_t n, int64_t B, int k,
-                              cudaStream_t st) {
+                              cudaStream_t st, uint64_t seed, uint64_t offset) {
     const int64_t total = n * B;
     const int al = aligned16(mu, sigma, eps, z, angles);      // null pointers count as aligned
     int64_t done = 0;
@@ -416,7 +455,7 @@ static int reparam_fwd_launch(const T* mu, const T* sigma, const T* eps, T* z, T
         int rc = pipe_grid(lv::so3_reparam_fwd_pipe_kernel<T, KT, EULER, TILE, NS>, TILE, SMEM, nfull, cap_cache, &grid);
         if (rc) return rc;
         if (grid > 0) {
-            lv::so3_reparam_fwd_pipe_kernel<T, KT, EULER, TILE, NS><<<grid, TILE, SMEM, st>>>(mu, sigma, eps, z, angles, log_q, nfull, B, k);
+            lv::so3_reparam_fwd_pipe_kernel<T, KT, EULER, TILE, NS><<<grid, TILE, SMEM, st>>>(mu, sigma, eps, z, angles, log_q, nfull, B, k, seed, offset);
             done = nfull * TILE;                              // the ragged tail (n == 1 only) follows below
         }
     }
@@ -424,15 +463,15 @@ static int reparam_fwd_launch(const T* mu, const T* sigma, const T* eps, T* z, T
         const int64_t rest = total - done;                    // done > 0 implies n == 1: the tail is its own (B = rest) problem
         const unsigned grid = unsigned((rest + TILE - 1) / TILE);
         lv::so3_reparam_fwd_kernel<T, KT, EULER, TILE><<<grid, TILE, 0, st>>>(
-            mu + (done ? done * 9 : 0), sigma + (done ? done * 3 : 0), eps + done * 3, z ? z + done * 9 : nullptr,
-            angles ? angles + done * 3 : nullptr, log_q ? log_q + done : nullptr, rest, done ? rest : B, k, al);
+            mu + (done ? done * 9 : 0), sigma + (done ? done * 3 : 0), eps ? eps + done * 3 : nullptr, z ? z + done * 9 : nullptr,
+            angles ? angles + done * 3 : nullptr, log_q ? log_q + done : nullptr, rest, done ? rest : B, k, al, seed, offset + uint64_t(done));
     }
     return LV_OK;
 }
 
 template <typename T, int KT, bool EULER, int TILE>
 static int reparam_bwd_launch(const T* mu, const T* sigma, const T* eps, const T* gz, const T* gangles, const T* glq, T* gmu,
-                              T* gsigma, int64_t n, int64_t B, int k, cudaStream_t st) {
+                              T* gsigma, int64_t n, int64_t B, int k, cudaStream_t st, uint64_t seed, uint64_t offset) {
     const int64_t total = n * B;
     const int al = aligned16(mu, sigma, eps, gz, gangles, gmu, gsigma);
     int64_t done = 0;
@@ -445,7 +484,7 @@ static int reparam_bwd_launch(const T* mu, const T* sigma, const T* eps, const T
         int rc = pipe_grid(lv::so3_reparam_bwd_pipe_kernel<T, KT, EULER, TILE, NS>, TILE, SMEM, nfull, cap_cache, &grid);
         if (rc) return rc;
         if (grid > 0) {
-            lv::so3_reparam_bwd_pipe_kernel<T, KT, EULER, TILE, NS><<<grid, TILE, SMEM, st>>>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, nfull, B, k);
+            lv::so3_reparam_bwd_pipe_kernel<T, KT, EULER, TILE, NS><<<grid, TILE, SMEM, st>>>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, nfull, B, k, seed, offset);
             done = nfull * TILE;
         }
     }
@@ -453,27 +492,28 @@ static int reparam_bwd_launch(const T* mu, const T* sigma, const T* eps, const T
         const int64_t rest = total - done;
         const unsigned grid = unsigned((rest + TILE - 1) / TILE);
         lv::so3_reparam_bwd_kernel<T, KT, EULER, TILE><<<grid, TILE, 0, st>>>(
-            mu + (done ? done * 9 : 0), sigma + (done ? done * 3 : 0), eps + done * 3, gz ? gz + done * 9 : nullptr,
+            mu + (done ? done * 9 : 0), sigma + (done ? done * 3 : 0), eps ? eps + done * 3 : nullptr, gz ? gz + done * 9 : nullptr,
             gangles ? gangles + done * 3 : nullptr, glq ? glq + done : nullptr, gmu + done * 9, gsigma + done * 3, rest,
-            done ? rest : B, k, al);
+            done ? rest : B, k, al, seed, offset + uint64_t(done));
     }
     return LV_OK;
 }
 
 template <typename T, bool EULER>
 static int reparam_fwd(const char* name, const T* mu, const T* sigma, const T* eps, T* z, T* angles,
-                       T* log_q, int64_t n, int64_t B, int k, void* stream) {
+                       T* log_q, int64_t n, int64_t B, int k, void* stream, bool philox = false, uint64_t seed = 0, uint64_t offset = 0) {
     int rc = reparam_check(name, n, B, k);
     if (rc) return rc;
     const int64_t total = n * B;
     if (total == 0) return LV_OK;
-    if (!mu || !sigma || !eps || (EULER ? !angles : !z)) { lv::set_error("%s: null pointer", name); return LV_ERR_ARG; }
+    if (!mu || !sigma || (!eps && !philox) || (EULER ? !angles : !z)) { lv::set_error("%s: null pointer", name); return LV_ERR_ARG; }
+    if (philox) eps = nullptr;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     constexpr int TILE = sizeof(T) == 8 ? lv::RP_TILE / 2 : lv::RP_TILE;
-    if constexpr (sizeof(T) == 8) rc = reparam_fwd_launch<T, 0, EULER, TILE>(mu, sigma, eps, z, angles, log_q, n, B, k, st);
-    else if (k == 3) rc = reparam_fwd_launch<T, 3, EULER, TILE>(mu, sigma, eps, z, angles, log_q, n, B, k, st);
-    else if (k == 10) rc = reparam_fwd_launch<T, 10, EULER, TILE>(mu, sigma, eps, z, angles, log_q, n, B, k, st);
-    else rc = reparam_fwd_launch<T, 0, EULER, TILE>(mu, sigma, eps, z, angles, log_q, n, B, k, st);
+    if constexpr (sizeof(T) == 8) rc = reparam_fwd_launch<T, 0, EULER, TILE>(mu, sigma, eps, z, angles, log_q, n, B, k, st, seed, offset);
+    else if (k == 3) rc = reparam_fwd_launch<T, 3, EULER, TILE>(mu, sigma, eps, z, angles, log_q, n, B, k, st, seed, offset);
+    else if (k == 10) rc = reparam_fwd_launch<T, 10, EULER, TILE>(mu, sigma, eps, z, angles, log_q, n, B, k, st, seed, offset);
+    else rc = reparam_fwd_launch<T, 0, EULER, TILE>(mu, sigma, eps, z, angles, log_q, n, B, k, st, seed, offset);
     if (rc) return rc;
     return lv::check_launch(name);
 }
@@ -481,18 +521,19 @@ static int reparam_fwd(const char* name, const T* mu, const T* sigma, const T* e
 template <typename T, bool EULER>
 static int reparam_bwd(const char* name, const T* mu, const T* sigma, const T* eps, const T* gz,
                        const T* gangles, const T* glq, T* gmu, T* gsigma, int64_t n, int64_t B, int k,
-                       void* stream) {
+                       void* stream, bool philox = false, uint64_t seed = 0, uint64_t offset = 0) {
     int rc = reparam_check(name, n, B, k);
     if (rc) return rc;
     const int64_t total = n * B;
     if (total == 0) return LV_OK;
-    if (!mu || !sigma || !eps || !gmu || !gsigma || (EULER && !gangles)) { lv::set_error("%s: null pointer", name); return LV_ERR_ARG; }
+    if (!mu || !sigma || (!eps && !philox) || !gmu || !gsigma || (EULER && !gangles)) { lv::set_error("%s: null pointer", name); return LV_ERR_ARG; }
+    if (philox) eps = nullptr;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     constexpr int TILE = sizeof(T) == 8 ? lv::RP_TILE / 2 : lv::RP_TILE;
-    if constexpr (sizeof(T) == 8) rc = reparam_bwd_launch<T, 0, EULER, TILE>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, n, B, k, st);
-    else if (k == 3) rc = reparam_bwd_launch<T, 3, EULER, TILE>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, n, B, k, st);
-    else if (k == 10) rc = reparam_bwd_launch<T, 10, EULER, TILE>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, n, B, k, st);
-    else rc = reparam_bwd_launch<T, 0, EULER, TILE>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, n, B, k, st);
+    if constexpr (sizeof(T) == 8) rc = reparam_bwd_launch<T, 0, EULER, TILE>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, n, B, k, st, seed, offset);
+    else if (k == 3) rc = reparam_bwd_launch<T, 3, EULER, TILE>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, n, B, k, st, seed, offset);
+    else if (k == 10) rc = reparam_bwd_launch<T, 10, EULER, TILE>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, n, B, k, st, seed, offset);
+    else rc = reparam_bwd_launch<T, 0, EULER, TILE>(mu, sigma, eps, gz, gangles, glq, gmu, gsigma, n, B, k, st, seed, offset);
     if (rc) return rc;
     return lv::check_launch(name);
 }
@@ -517,3 +558,33 @@ static int reparam_bwd(const char* name, const T* mu, const T* sigma, const T* e
     }
 LV_REPARAM_ENTRY(f32, float)
 LV_REPARAM_ENTRY(f64, double)
+
+/* in-kernel noise: eps ~ N(0,1) is generated per sample from (seed, offset + flat sample index) -- forward and backward draw  \
+   the same numbers, lv_philox_normal_* writes them out.  angles == NULL: plain reparameterize (z required);                  \
+   angles != NULL: fused with matrix -> ZYZ Euler (z optional). */
+#define LV_REPARAM_PHILOX_ENTRY(SFX, T)                                                                                          \
+    extern "C" int lv_so3_reparam_philox_fwd_##SFX(const T* mu, const T* sigma, int64_t seed, int64_t offset, T* z, T* angles,   \
+                                                   T* log_q, int64_t n, int64_t B, int k, void* stream) {                        \
+        if (angles) return reparam_fwd<T, true>("so3_reparam_philox_fwd", mu, sigma, nullptr, z, angles, log_q, n, B, k, stream, \
+                                                true, uint64_t(seed), uint64_t(offset));                                         \
+        return reparam_fwd<T, false>("so3_reparam_philox_fwd", mu, sigma, nullptr, z, nullptr, log_q, n, B, k, stream, true,     \
+                                     uint64_t(seed), uint64_t(offset));                                                          \
+    }                                                                                                                            \
+    extern "C" int lv_so3_reparam_philox_bwd_##SFX(const T* mu, const T* sigma, int64_t seed, int64_t offset, const T* gz,       \
+                                                   const T* gangles, const T* glq, T* gmu, T* gsigma, int64_t n, int64_t B,      \
+                                                   int k, void* stream) {                                                        \
+        if (gangles) return reparam_bwd<T, true>("so3_reparam_philox_bwd", mu, sigma, nullptr, gz, gangles, glq, gmu, gsigma, n, \
+                                                 B, k, stream, true, uint64_t(seed), uint64_t(offset));                          \
+        return reparam_bwd<T, false>("so3_reparam_philox_bwd", mu, sigma, nullptr, gz, nullptr, glq, gmu, gsigma, n, B, k,       \
+                                     stream, true, uint64_t(seed), uint64_t(offset));                                            \
+    }                                                                                                                            \
+    extern "C" int lv_philox_normal_##SFX(T* out, int64_t rows, int64_t seed, int64_t offset, void* stream) {                    \
+        if (rows < 0) { lv::set_error("philox_normal: negative size"); return LV_ERR_ARG; }                                      \
+        if (rows == 0) return LV_OK;                                                                                             \
+        if (!out) { lv::set_error("philox_normal: null pointer"); return LV_ERR_ARG; }                                           \
+        lv::philox_normal_kernel<T><<<unsigned((rows + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(           \
+            out, rows, uint64_t(seed), uint64_t(offset));                                                                        \
+        return lv::check_launch("philox_normal");                                                                                \
+    }
+LV_REPARAM_PHILOX_ENTRY(f32, float)
+LV_REPARAM_PHILOX_ENTRY(f64, double)

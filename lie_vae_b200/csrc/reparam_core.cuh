@@ -27,6 +27,43 @@ __device__ __forceinline__ double rp_exp2s(double x) { return ::exp(x); }
 __device__ __forceinline__ float winding_theta(float theta, float k) { return theta + __fmul_rn(float(RP_TWO_PI), k); }
 __device__ __forceinline__ double winding_theta(double theta, double k) { return theta + __dmul_rn(RP_TWO_PI, k); }
 
+// ------------------------------------------------------------------ in-kernel noise (Philox4x32-10, keyed by the sample index)
+// The reference draws eps ~ N(0, 1) of shape (n, B, 3) from torch's global generator (reparameterize.py:137-141) and pins no
+// stream, so any reproducible N(0, 1) source is admissible.  With eps == nullptr the kernels generate it: counter = global
+// flat sample index (+ offset), key = seed, one Philox block per sample -> Box-Muller -> three normals.  The backward
+// regenerates the same numbers, so eps never exists in memory (12 of the 60 input bytes per sample); lv_philox_normal_*
+// materialises the identical stream for tests and for callers that want to inspect it.
+__device__ __forceinline__ void philox4x32_10(uint64_t ctr, uint64_t key, uint32_t (&x)[4]) {
+    uint32_t c0 = uint32_t(ctr), c1 = uint32_t(ctr >> 32), c2 = 0u, c3 = 0u;
+    uint32_t k0 = uint32_t(key), k1 = uint32_t(key >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    x[0] = c0; x[1] = c1; x[2] = c2; x[3] = c3;
+}
+// three N(0, 1) samples of flat sample index `index`: u = (x + 0.5) 2^-32 in (0, 1); Box-Muller on (x0, x1) and (x2, x3)
+template <typename T>
+__device__ __forceinline__ void philox_normal3(uint64_t seed, uint64_t index, T (&ep)[3]) {
+    uint32_t x[4];
+    philox4x32_10(index, seed, x);
+    const float u0 = (float(x[0] >> 8) + 0.5f) * 5.9604644775390625e-08f;     // 24 bits: exact in float, never 0 or 1
+    const float u2 = (float(x[2] >> 8) + 0.5f) * 5.9604644775390625e-08f;
+    const float a1 = float(x[1]) * 4.656612873077392578125e-10f;               // 2 u in [0, 2]: the angle 2 pi u as pi * a
+    const float a3 = float(x[3]) * 4.656612873077392578125e-10f;
+    const float r0 = sqrtf(-2.0f * logf(u0)), r2 = sqrtf(-2.0f * logf(u2));
+    float s1, c1, s3, c3;
+    sincospif(a1, &s1, &c1);
+    sincospif(a3, &s3, &c3);
+    ep[0] = T(r0 * c1);
+    ep[1] = T(r0 * s1);
+    ep[2] = T(r2 * c3);
+    (void)s3;
+}
+
 // ------------------------------------------------------------------ wrapped log-density terms
 // Term k of the winding sum is  t_k = -a x_k + log max(x_k, c),  x_k = (theta + 2 pi k)^2  (reparameterize.py:246-259), so
 //   exp(t_k - ref) = max(x_k, c) * E_k,   E_k = exp(-a (x_k - x_ref)),

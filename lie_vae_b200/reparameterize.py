@@ -45,6 +45,17 @@ def so3_reparameterize_eazyz(mu, sigma, eps, k=10):
     return _ops.SO3ReparamEazyz.apply(mu, sigma, eps, k)
 
 
+def so3_reparameterize_philox(mu, sigma, n=1, k=10, seed=0, offset=0, euler=False):
+    """The fused kernel with IN-KERNEL noise: eps ~ N(0,1) of ``reparameterize.py:137-141`` is generated per sample by
+    Philox4x32-10 (key ``seed``, counter ``offset`` + flat sample index) and regenerated in the backward, so it never
+    exists in memory.  Returns (z (n,B,3,3) -- or its ZYZ Euler angles (n,B,3) with ``euler`` --, log_q (n,B)).
+    ``philox_normal(n * B, seed, offset).view(n, B, 3)`` is the eps it uses (same bits)."""
+    return _ops.SO3ReparamPhilox.apply(mu, sigma, n, k, seed, offset, euler)
+
+
+philox_normal = _ops.philox_normal
+
+
 _HALF_LOG_2PI = 0.5 * math.log(2 * math.pi)
 
 
@@ -288,18 +299,39 @@ class SO3reparameterize(nn.Module):
         assert self.reparameterize.z_dim == 3
         self.k = k
         self.return_means = False
+        self._v, self._philox = None, None
         self.mu_lie, self.v, self.z = None, None, None
         self._log_q = None
+        # in_kernel_noise: eps is generated inside the kernel (Philox keyed by torch's seed, counter = samples drawn so far)
+        # instead of being drawn by torch and stored -- the throughput mode of SURVEY.md section 7; the unfused path only
+        self.in_kernel_noise = False
+        self._noise_offset = 0
         # encoder heads (Linear + mean map, Linear + softplus) inside the reparameterize kernel when the mean module
         # is one of the four reference mean maps on float32 CUDA features; set False for the unfused launches
         self.fuse_heads = True
-        self._fused_input = None
+        self._fused = False                                 # whether the last forward ran the fused-head kernel
+
+    @property
+    def v(self):
+        """Algebra sample eps * sigma (n,B,3) (``reparameterize.py:222``); with in-kernel noise it is materialised on demand."""
+        if self._v is None and self._philox is not None:
+            seed, offset, n, B = self._philox
+            rep = self.reparameterize
+            rep.eps = _ops.philox_normal(n * B, seed, offset, dtype=rep.sigma.dtype, device=rep.sigma.device).view(n, B, 3)
+            self._v = rep.eps * rep.sigma
+            rep.z = self._v
+        return self._v
+
+    @v.setter
+    def v(self, value):
+        self._v = value
+        self._philox = None
 
     def _fused_head_mode(self, x):
         """'alg' / 'q' / 's2s2' when the encoder heads can run inside the reparameterize kernel, else None."""
         mode = {AlgebraMean: "alg", QuaternionMean: "q", S2S2Mean: "s2s2", S2S1Mean: "s2s1"}.get(type(self.mean_module))
         rep = self.reparameterize
-        ok = (self.fuse_heads and mode is not None and type(rep) is N0reparameterize and rep.fixed_sigma is None
+        ok = (self.fuse_heads and not self.in_kernel_noise and mode is not None and type(rep) is N0reparameterize and rep.fixed_sigma is None
               and not self.return_means and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2
               and x.shape[1] <= _ops.HEAD_MAX_DIN and rep.sigma_linear.weight.dtype == torch.float32)
         return mode if ok else None
@@ -317,19 +349,27 @@ class SO3reparameterize(nn.Module):
             wm, bm = mean.map.weight, mean.map.bias
         self.z, self._log_q, self.mu_lie, rep.sigma = _ops.SO3HeadReparam.apply(
             x, wm, bm, rep.sigma_linear.weight, rep.sigma_linear.bias, rep.eps, mode, self.k, False)
-        self._fused_input = (x, mode)                       # nsample() re-runs the heads so that gradients keep flowing
         self.v = rep.eps * rep.sigma
         rep.z = self.v
+        self._fused = True
         return self.z
 
     def forward(self, x, n=1):
         mode = self._fused_head_mode(x)
         if mode is not None:
             return self._forward_fused(x, n, mode)
-        self._fused_input = None
+        self._fused = False
         self.mu_lie = self.mean_module(x)
         rep = self.reparameterize
         rep.sigma = rep.compute_sigma(x)
+        if self.in_kernel_noise and not self.return_means and type(rep) is N0reparameterize:
+            B = rep.sigma.shape[0]
+            seed, offset = torch.initial_seed() & 0x7FFFFFFFFFFFFFFF, self._noise_offset
+            self._noise_offset += n * B
+            self.z, self._log_q = so3_reparameterize_philox(self.mu_lie, rep.sigma, n, self.k, seed, offset)
+            self._v, self._philox = None, (seed, offset, n, B)      # v / eps are materialised only if somebody reads them
+            rep.eps, rep.z = None, None
+            return self.z
         rep.eps = rep.sample_noise(n)
         self.z, self._log_q = so3_reparameterize(self.mu_lie, rep.sigma, rep.eps, self.k)
         self.v = rep.eps * rep.sigma          # attribute parity; not consumed by the kernel path
@@ -339,18 +379,12 @@ class SO3reparameterize(nn.Module):
         return self.z
 
     def nsample(self, n=1):
-        """Draw fresh noise for the cached mu / sigma (``reparameterize.py:269-273``)."""
+        """``mu_lie @ rodrigues(v)`` for the cached algebra sample (``reparameterize.py:269-273``): like the reference a
+        pure function of the module's cached state -- no fresh noise, nothing overwritten (``forward`` itself obtains z
+        from the fused kernel)."""
         if self.return_means:
             return self.mu_lie.expand(n, *[-1] * len(self.mu_lie.shape))
-        if getattr(self, "_fused_input", None) is not None:
-            x, mode = self._fused_input
-            return self._forward_fused(x, n, mode)
-        rep = self.reparameterize
-        rep.eps = rep.sample_noise(n)
-        self.v = rep.eps * rep.sigma
-        rep.z = self.v
-        z, self._log_q = so3_reparameterize(self.mu_lie, rep.sigma, rep.eps, self.k)
-        return z
+        return self.mu_lie @ rodrigues(self.v)
 
     def kl(self):
         log_q_z_x = self.log_posterior()

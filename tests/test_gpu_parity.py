@@ -47,12 +47,12 @@ def frac_outside(a, d, rtol=RTOL, atol=ATOL):
     return float(np.mean(np.abs(a - d) > atol + rtol * np.abs(d)))
 
 
-def as_good_as_ref32(ours, ref64, ref32, what):
+def as_good_as_ref32(ours, ref64, ref32, what, floor=1.0):
     """ours (fp32 kernel) must be at least as close to the fp64 truth as the reference's own fp32 arithmetic
     (the oracle run in fp32).  Tolerances are relative to the tensor's scale (atol = 1e-5 * max(1, rms)), and
     ill-conditioned elements (atan2 near its cut, acos near the clamp, cancelling sums) may differ in *which*
     elements exceed the tolerance, so the comparison is on the fraction of outliers (<= 1.25x the reference's, +10 ppm
-    or one element of slack) and on the worst error (<= 2x the reference's worst, or the tolerance floor)."""
+    or one element of slack) and on the worst error (<= 2x the reference's worst, or ``floor`` x the north-star atol)."""
     ours = ours.detach().double().cpu().numpy()
     ref64 = ref64.detach().double().cpu().numpy()
     ref32 = ref32.detach().double().cpu().numpy()
@@ -64,7 +64,7 @@ def as_good_as_ref32(ours, ref64, ref32, what):
     e_ours, e_ref = np.abs(ours - ref64).max(), np.abs(ref32 - ref64).max()
     slack = max(1e-5, 1.0 / max(ours.size, 1))
     assert f_ours <= 1.25 * f_ref + slack, "%s: %.3g of elements outside tol (reference fp32: %.3g)" % (what, f_ours, f_ref)
-    assert e_ours <= max(2 * e_ref, 4 * atol), "%s: max abs err %.3g (reference fp32: %.3g)" % (what, e_ours, e_ref)
+    assert e_ours <= max(2 * e_ref, floor * atol), "%s: max abs err %.3g (reference fp32: %.3g)" % (what, e_ours, e_ref)
 
 
 def run_fn(fn, inputs, w, dtype):

@@ -608,6 +608,7 @@ def test_fused_heads_match_unfused_modules(mods, mode, n, B, Din, k):
     x0 = torch.randn(B, Din, device="cuda")
     eps = torch.randn(n, B, 3, device="cuda")
     wz, wl = torch.randn(n, B, 3, 3, device="cuda"), torch.randn(n, B, device="cuda")
+    wm, ws = torch.randn(B, 3, 3, device="cuda"), torch.randn(B, 3, device="cuda")
     res = []
     for fuse in (True, False):
         mod.fuse_heads = fuse
@@ -615,8 +616,10 @@ def test_fused_heads_match_unfused_modules(mods, mode, n, B, Din, k):
         mod.reparameterize.sample_noise = lambda n_=1, like=None: eps
         x = x0.clone().requires_grad_(True)
         z = mod(x, n)
-        assert (mod._fused_input is not None) == fuse
-        ((z * wz).sum() + (mod.log_posterior() * wl).sum() + mod.kl().sum().float()).backward()
+        assert mod._fused == fuse
+        # mu_lie and sigma are differentiable on both paths: regularisers / kl terms built from them reach the heads
+        ((z * wz).sum() + (mod.log_posterior() * wl).sum() + mod.kl().sum().float()
+         + (mod.mu_lie * wm).sum() + (mod.reparameterize.sigma * ws).sum() + mod.reparameterize.kl().sum()).backward()
         res.append((z.detach(), mod.log_posterior().detach(), mod.mu_lie.detach(), mod.reparameterize.sigma.detach(), x.grad,
                     {k_: p.grad.clone() for k_, p in mod.named_parameters()}))
     (z1, lq1, mu1, sg1, gx1, gp1), (z2, lq2, mu2, sg2, gx2, gp2) = res
@@ -629,36 +632,54 @@ def test_fused_heads_match_unfused_modules(mods, mode, n, B, Din, k):
         assert (a - b).abs().max().item() <= 2e-3 * scale, what
 
 
-def test_fused_heads_functional_euler_and_oracle(mods):
-    """so3_head_reparameterize(..., euler=True) against the float64 oracle composition (Linear -> rodrigues, softplus ->
-    reparameterize -> Euler) including the gradients of features, weight and bias."""
+@pytest.mark.parametrize("mode", ["alg", "q", "s2s1", "s2s2"])
+@pytest.mark.parametrize("euler", [True, False])
+def test_fused_heads_functional_vs_oracle(mods, mode, euler):
+    """so3_head_reparameterize (every mean map, pose as z or as Euler angles) against the float64 oracle composition
+    (Linear -> mean map, softplus -> reparameterize [-> Euler]) including the gradients of features, weights and biases,
+    with gradient also arriving through the mu / sigma outputs."""
     _, rp, _ = mods
     torch.manual_seed(9)
     B, Din, n, k = 700, 10, 2, 3
+    dm = {"alg": 3, "q": 4, "s2s1": 5, "s2s2": 6}[mode]
     h64 = torch.randn(B, Din, dtype=torch.float64)
-    W64, b64 = torch.randn(6, Din, dtype=torch.float64) * 0.5, torch.randn(6, dtype=torch.float64) * 0.5
+    W64, b64 = torch.randn(dm + 3, Din, dtype=torch.float64) * 0.5, torch.randn(dm + 3, dtype=torch.float64) * 0.5
     eps64 = torch.randn(n, B, 3, dtype=torch.float64)
-    wa, wl = torch.randn(n, B, 3, dtype=torch.float64), torch.randn(n, B, dtype=torch.float64)
+    wp = torch.randn((n, B, 3) if euler else (n, B, 3, 3), dtype=torch.float64)
+    wl, wm, ws = torch.randn(n, B, dtype=torch.float64), torch.randn(B, 3, 3, dtype=torch.float64), torch.randn(B, 3, dtype=torch.float64)
+
+    def mean_map(pre):
+        if mode == "alg":
+            return O.rodrigues(pre)
+        if mode == "q":
+            return O.quaternions_to_group_matrix(pre)
+        if mode == "s2s1":
+            s2, s1 = pre[:, :3], pre[:, 3:]
+            return O.s2s1rodrigues(s2 / s2.norm(p=2, dim=-1, keepdim=True), s1 / s1.norm(p=2, dim=-1, keepdim=True))
+        v = pre.double().view(-1, 2, 3)                     # reparameterize.py:195-197: Gram-Schmidt in float64, cast back
+        return O.s2s2_gram_schmidt(v[:, 0], v[:, 1]).to(pre.dtype)
 
     def run(dtype, dev):
         h, W, b = (t.detach().clone().to(dtype).to(dev).requires_grad_(True) for t in (h64, W64, b64))
         eps = eps64.to(dtype).to(dev)
         if dev == "cuda":
-            ang, lq, mu, sg = rp.so3_head_reparameterize(h, W[:3], b[:3], W[3:], b[3:], eps, "alg", k, euler=True)
+            pose, lq, mu, sg = rp.so3_head_reparameterize(h, W[:dm], b[:dm], W[dm:], b[dm:], eps, mode, k, euler=euler)
         else:
             pre = h @ W.t() + b
-            mu, sg = O.rodrigues(pre[:, :3]), torch.nn.functional.softplus(pre[:, 3:])
-            z, lq = O.so3_reparameterize(mu, sg, eps, k)
-            ang = O.group_matrix_to_eazyz(z)
-        ((ang * wa.to(dtype).to(dev)).sum() + (lq * wl.to(dtype).to(dev)).sum()).backward()
-        return [t.detach().double().cpu() for t in (ang, lq, mu, sg, h.grad, W.grad, b.grad)]
+            mu, sg = mean_map(pre[:, :dm]), torch.nn.functional.softplus(pre[:, dm:])
+            pose, lq = O.so3_reparameterize(mu, sg, eps, k)
+            if euler:
+                pose = O.group_matrix_to_eazyz(pose)
+        c = lambda t: t.to(dtype).to(dev)
+        ((pose * c(wp)).sum() + (lq * c(wl)).sum() + (mu * c(wm)).sum() + (sg * c(ws)).sum()).backward()
+        return [t.detach().double().cpu() for t in (pose, lq, mu, sg, h.grad, W.grad, b.grad)]
     got, ref, ref32 = run(torch.float32, "cuda"), run(torch.float64, "cpu"), run(torch.float32, "cpu")
-    names = ["angles", "log_q", "mu", "sigma", "g_h", "g_W", "g_b"]
+    names = ["pose", "log_q", "mu", "sigma", "g_h", "g_W", "g_b"]
     for nm, a, b, c in zip(names, got, ref, ref32):
         if nm in ("mu", "sigma"):
             close(a, b, 1e-5, 2e-6, nm)
         else:
-            as_good_as_ref32(a, b, c, nm)
+            as_good_as_ref32(a, b, c, "%s/%s" % (mode, nm))
 
 
 def test_fused_heads_nsample_and_fallbacks(mods):
@@ -666,16 +687,20 @@ def test_fused_heads_nsample_and_fallbacks(mods):
     torch.manual_seed(2)
     mod = rp.SO3reparameterize(rp.N0reparameterize(10, 3), rp.AlgebraMean(10), k=3).cuda()
     x = torch.randn(40, 10, device="cuda", requires_grad=True)
-    mod(x, 2)
-    z = mod.nsample(4)                                        # fresh noise, gradients still reach the encoder features
-    assert tuple(z.shape) == (4, 40, 3, 3)
-    z.sum().backward()
+    z0 = mod(x, 2)
+    lq0, v0 = mod.log_posterior().detach().clone(), mod.v.detach().clone()
+    z = mod.nsample(4)      # reparameterize.py:269-273: a pure function of the cached mu_lie / v -- same sample, nothing overwritten
+    assert tuple(z.shape) == (2, 40, 3, 3)
+    close(z, z0, 1e-5, 5e-6, "nsample")
+    assert torch.equal(mod.log_posterior(), lq0) and torch.equal(mod.v, v0) and mod.z is z0
+    z.sum().backward()      # mu_lie and sigma are differentiable outputs of the fused kernel: gradients reach the features
     assert x.grad is not None and x.grad.abs().sum().item() > 0 and mod.mean_module.map.weight.grad is not None
+    assert mod.reparameterize.sigma_linear.weight.grad is not None
     # paths the fused kernel does not cover fall back to the separate launches: fixed sigma, wide features, float64
     for m2, xin in ((rp.SO3reparameterize(rp.N0reparameterize(10, 3, fixed_sigma=0.3), rp.AlgebraMean(10)).cuda(), torch.randn(8, 10, device="cuda")),
                     (rp.SO3reparameterize(rp.N0reparameterize(40, 3), rp.AlgebraMean(40)).cuda(), torch.randn(8, 40, device="cuda")),
                     (rp.SO3reparameterize(rp.N0reparameterize(10, 3), rp.QuaternionMean(10)).cuda().double(), torch.randn(8, 10, device="cuda", dtype=torch.float64))):
         out = m2(xin)
-        assert m2._fused_input is None and tuple(out.shape) == (1, 8, 3, 3) and tuple(m2.kl().shape) == (8,)
+        assert not m2._fused and tuple(out.shape) == (1, 8, 3, 3) and tuple(m2.kl().shape) == (8,)
     mod.deterministic()
     assert torch.equal(mod(x)[0], mod.mu_lie)
