@@ -19,9 +19,10 @@ over-determined set of unit vectors and solving the (exactly consistent) linear
 system in float64, then zeroing entries below 1e-12.  Known closed forms
 (J_0..J_3) are checked in ``tests/test_jmatrix.py``.
 
-Nothing here touches the GPU; the table is uploaded once through
-``lv_wigner_set_j`` for the generic kernels and baked into
-``csrc/wigner_gen.cuh`` by ``tools/gen_wigner.py`` for the unrolled, packed ones.
+Nothing here touches the GPU: the generic kernels take the packed table as a
+caller-owned device pointer (``lv_wigner_generic_*``, ``_ops._j_table``), and
+``tools/gen_wigner.py`` bakes it into ``csrc/wigner_gen.cuh`` for the unrolled,
+packed ones.  Independent check: ``tests/test_wigner_independent.py``.
 """
 from functools import lru_cache
 import math

@@ -16,8 +16,14 @@ values and autograd gradients); ``tests/test_oracle_golden.py`` checks this
 module against them to 1e-12.  The Wigner J table is the one third-party input
 the reference does not ship (lie_learn, unpinned, absent): with respect to
 lie_learn's own table the Wigner values are *parity unpinned*; they are pinned
-instead by closed-form J_0..J_3, J=J^T, J^2=I and the reference's own
-orthogonality / inverse / anti-homomorphism tests (``lie_tools.py:337-357``).
+instead by the definition of the representation itself: ``oracle/wigner_direct.py``
+builds D^l(a,b,c) for l <= 8 from scipy's spherical harmonics with no J anywhere
+(``Y(R p) = D Y(p)``, the real basis lie_learn documents) and
+``tests/test_wigner_independent.py`` holds ``wigner_d_matrix`` to it at 1e-10; the
+J used here comes from the same J-free construction, not from the product's
+``lie_vae_b200/jmatrix.py`` (the two are compared at 1e-12).  Also: closed-form
+J_0..J_3, J=J^T, J^2=I and the reference's own orthogonality / inverse /
+anti-homomorphism tests (``lie_tools.py:337-357``).
 """
 import math
 
@@ -160,18 +166,10 @@ def random_group_matrices(n, dtype=torch.float32, device=None, generator=None):
 
 # --------------------------------------------------------------------------- Wigner
 def _j_np(l):
-    # the table is regenerated from its definition; see the module docstring.
-    import importlib.util
-    import os
-    here = os.path.dirname(os.path.abspath(__file__))
-    path = os.path.join(os.path.dirname(here), "lie_vae_b200", "jmatrix.py")
-    mod = _j_np.__dict__.get("mod")
-    if mod is None:
-        spec = importlib.util.spec_from_file_location("_oracle_jmatrix", path)
-        mod = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(mod)
-        _j_np.mod = mod
-    return mod.j_matrix_np(l)
+    # the oracle's own J source: the representation matrix of (x,y,z) -> (x,-z,-y) on scipy's spherical harmonics
+    # (oracle/wigner_direct.py) -- independent of the product's lie_vae_b200/jmatrix.py, which tests compare it with.
+    from . import wigner_direct
+    return wigner_direct.j_matrix_direct(int(l))
 
 
 def j_matrix(l, dtype=torch.float64, device=None):

@@ -8,7 +8,9 @@ Every fixture stores the seeded inputs, the reference's outputs and, where the
 function is differentiable, the reference's autograd gradients of the scalar
 ``sum(out * w)`` for stored random weights ``w``.  The reference is imported
 through ``tests/refshim.py`` (stand-ins for three absent third-party packages;
-the Wigner J table is the regenerated one, see ``lie_vae_b200/jmatrix.py``).
+the Wigner J table stand-in is the J-free construction of ``oracle/wigner_direct.py``; the committed files were
+written when it still was the product's ``lie_vae_b200/jmatrix.py`` table -- regenerating with the independent one
+reproduces them to 3.6e-13, they are held to 1e-11).
 """
 import math
 import os

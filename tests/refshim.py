@@ -4,7 +4,10 @@ Test infrastructure only.  The reference needs three third-party packages that
 are absent offline; stand-ins are placed in ``sys.modules``:
 
 * ``hyperspherical_vae_pytorch.distributions`` (only used by the out-of-scope vMF path),
-* ``lie_learn...pinchon_hoggan_dense.Jd`` backed by the regenerated J table,
+* ``lie_learn...pinchon_hoggan_dense.Jd`` backed by the J-free construction of ``oracle/wigner_direct.py`` (scipy's
+  spherical harmonics; NOT the product's ``lie_vae_b200/jmatrix.py``, which ``tests/test_wigner_independent.py`` compares
+  with it at 1e-12 -- the committed fixtures were generated when the stand-in still used the product table; the two agree to
+  2e-15, far below the 1e-11 the fixtures are held to),
 * ``lie_learn.groups.SO3.change_coordinates`` (image loading only).
 
 ``/root/reference`` does not exist on the GPU box: everything that uses this
@@ -23,9 +26,12 @@ def reference_available():
 
 class _JTable:
     def __getitem__(self, l):
-        from lie_vae_b200.jmatrix import j_matrix_np
         import numpy as np
-        return np.array(j_matrix_np(l))
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        if root not in sys.path:
+            sys.path.insert(0, root)
+        from oracle.wigner_direct import j_matrix_direct
+        return np.array(j_matrix_direct(l))
 
 
 def _install_shims():
@@ -75,11 +81,9 @@ def load_reference(float64_j=True):
 
     if float64_j and not hasattr(lt, "_j_dtype"):
         lt._j_dtype = torch.float32
-        import numpy as np
-        from lie_vae_b200.jmatrix import j_matrix_np
+        jd = sys.modules["lie_learn.representations.SO3.pinchon_hoggan.pinchon_hoggan_dense"].Jd
 
-        def j_matrix(l, device=None):
-            return torch.tensor(np.array(j_matrix_np(l)), dtype=lt._j_dtype,
-                                device=torch.device(device))
+        def j_matrix(l, device=None):       # lie_tools.py:10-14 with the dtype made a switch; same Jd stand-in as above
+            return torch.tensor(jd[l], dtype=lt._j_dtype, device=torch.device(device))
         lt.j_matrix = j_matrix
     return lt, rp, dc
