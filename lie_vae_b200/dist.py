@@ -10,7 +10,7 @@ GPUs, gloo in the CPU tests).
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_bounds", "pack_reduction", "unpack_reduction", "allreduce_loss_and_grad"]
+__all__ = ["shard_bounds", "pack_reduction", "unpack_reduction", "allreduce_packed", "allreduce_loss_and_grad"]
 
 
 def shard_bounds(total, world_size, rank, multiple=1):
@@ -51,9 +51,15 @@ def unpack_reduction(buf, shape):
     return buf[0], buf[1:].reshape(shape)
 
 
-def allreduce_loss_and_grad(loss, grad_item_rep, group=None, out=None):
-    """Sum the local loss and item_rep gradient over all ranks; a no-op without a process group."""
-    buf = pack_reduction(loss, grad_item_rep, out)
+def allreduce_packed(buf, group=None):
+    """The path's one collective: all-reduce(sum) of an already packed ``[loss, grad item_rep]`` buffer, in place
+    (a step captured in a CUDA graph packs inside the graph and reduces outside it).  A no-op without a process group."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    return buf
+
+
+def allreduce_loss_and_grad(loss, grad_item_rep, group=None, out=None):
+    """Sum the local loss and item_rep gradient over all ranks; a no-op without a process group."""
+    buf = allreduce_packed(pack_reduction(loss, grad_item_rep, out), group)
     return unpack_reduction(buf, grad_item_rep.shape)
