@@ -204,6 +204,12 @@ def gen_inputs(lo, hi, dev, lt):
     return mu, sigma, eps, glq
 
 
+def step_loss(item, g_item, log_q, g_log_q):
+    a = (item.double() * g_item.double()).sum()
+    b = (log_q.view(-1, GEN_CHUNK) * g_log_q.view(-1, GEN_CHUNK)).sum(1).double().sum()
+    return (a + b).float()
+
+
 def bind_to_gpu_numa_node(index):
     """Run this rank on the CPUs next to its GPU (NVML's ideal affinity) BEFORE the pinned staging buffers are allocated:
     first-touch then places them on the GPU's NUMA node and eight ranks do not pull their inputs across the socket link."""
@@ -320,8 +326,10 @@ def run_ours(args):
             step_obj.decode_forward(a, b, item, y[i % 2])
             step_obj.decode_backward(a, b, item, gy[(g_first + i) % NBUF], accumulate=True)
         step_obj.latent_backward(mu, sigma, eps, glq, g_mu, g_sigma)
-        # loss = sum(y * g_y) + sum(log_q * g_lq);  y is linear in item_rep, so sum(y * g_y) = <item_rep, grad item_rep>
-        lvdist.pack_reduction((item * g_item).sum() + torch.dot(log_q, glq), g_item, out=red)
+        # loss = sum(y * g_y) + sum(log_q * g_lq);  y is linear in item_rep, so sum(y * g_y) = <item_rep, grad item_rep>.
+        # The two terms are large and cancel: partial sums per GLOBAL generation chunk, then float64, so that the scalar does
+        # not depend on how the batch is cut into ranks beyond the rounding of grad item_rep itself.
+        lvdist.pack_reduction(step_loss(item, g_item, log_q, glq), g_item, out=red)
 
     # The rank-local part of a step is a fixed sequence of launches on caller-owned buffers: capture it once in a CUDA
     # graph and replay it (no per-launch CPU cost, no gaps between the kernels); the one collective stays outside.
@@ -373,6 +381,7 @@ def run_ours(args):
     elapsed_ms = t0.elapsed_time(t1)
     loss_value = float(red[0])
     g_item_norm = float(red[1:].double().norm())
+    loss_term_a = float((item.double().view(-1) * red[1:].double()).sum())
     # per-kernel durations: a separate, un-timed pass of plain launches bracketed by CUDA events on the launching stream
     step_obj.enable_kernel_timing(True)
     for _ in range(2):
@@ -405,23 +414,27 @@ def run_ours(args):
     out_h = torch.empty(1 + M * CHANNELS).pin_memory()
     item_p = item.clone().requires_grad_(True)
 
-    def e2e_step():
-        item_p.grad = None
-        loss_acc = torch.zeros((), device=dev)
-        main = torch.cuda.current_stream()
+    def issue(i):
+        b = i % NST
+        sl = slice(i * e_micro, (i + 1) * e_micro)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[b])
+            stage[b][0].copy_(mu_h[sl], non_blocking=True)
+            stage[b][1].copy_(sg_h[sl], non_blocking=True)
+            ready[b].record(copy_stream)
 
-        def issue(i):
-            b = i % NST
-            sl = slice(i * e_micro, (i + 1) * e_micro)
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(freed[b])
-                stage[b][0].copy_(mu_h[sl], non_blocking=True)
-                stage[b][1].copy_(sg_h[sl], non_blocking=True)
-                ready[b].record(copy_stream)
-        for b in range(NST):
-            freed[b].record(main)
-        for i in range(min(NST - 1, e_n_micro)):
-            issue(i)
+    def e2e_step(prefetched, prefetch_next):
+        """One step; every micro-batch's mu / sigma travel host -> device inside it.  ``prefetch_next``: the copies of the NEXT
+        step's first micro-batches are issued before this step's result is read back (a loader that stays one batch ahead),
+        so only the first timed step pays the fill of the staging ring."""
+        item_p.grad = None
+        loss_acc = torch.zeros((), device=dev, dtype=torch.float64)
+        main = torch.cuda.current_stream()
+        if not prefetched:
+            for b in range(NST):
+                freed[b].record(main)
+            for i in range(min(NST - 1, e_n_micro)):
+                issue(i)
         for i in range(e_n_micro):
             b = i % NST
             if i + NST - 1 < e_n_micro:
@@ -435,26 +448,29 @@ def run_ours(args):
             # to autograd directly, exactly as a downstream module's backward would
             glq_i = glq[i * e_micro:(i + 1) * e_micro]
             torch.autograd.backward([yy, lq], [gy_for(i).view(e_micro, M, CHANNELS), glq_i.view(1, e_micro)])
-            loss_acc += torch.dot(lq.detach()[0], glq_i)
+            loss_acc += (lq.detach()[0].view(-1, GEN_CHUNK) * glq_i.view(-1, GEN_CHUNK)).sum(1).double().sum()
             stage[b][0].grad = None
             stage[b][1].grad = None
             stage[b][0].requires_grad_(False)
             stage[b][1].requires_grad_(False)
             freed[b].record(main)
+        if prefetch_next:
+            for i in range(min(NST - 1, e_n_micro)):
+                issue(i)
         # loss = sum(y * g_y) + sum(log_q * g_lq), with sum(y * g_y) = <item_rep, grad item_rep> (y is linear in item_rep)
-        lvdist.pack_reduction(loss_acc + (item_p.detach() * item_p.grad).sum(), item_p.grad, out=red)
+        lvdist.pack_reduction((loss_acc + (item_p.detach().double() * item_p.grad.double()).sum()).float(), item_p.grad, out=red)
         all_reduce_step_result()
         out_h.copy_(red, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(out_h[0])
 
     e2e_steps = max(1, args.e2e_steps)
-    e2e_step()
+    e2e_step(False, False)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(e2e_steps):
-        e2e_loss = e2e_step()
+    for it in range(e2e_steps):
+        e2e_loss = e2e_step(it > 0, it + 1 < e2e_steps)
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1) / e2e_steps
@@ -500,7 +516,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": n_loc * 48, "d2h_bytes_per_step": 4 * (1 + M * CHANNELS),
                     "micro_batch": e_micro, "copies_in_flight": NST - 1, "cpus_bound_to_gpu_numa_node": cpus_bound,
                     "api": "so3_reparameterize_philox(euler) -> WignerApply (torch.autograd); pinned host mu/sigma (48 B/sample), noise "
-                           "generated in the kernel; 4-deep staging ring"},
+                           "generated in the kernel; 4-deep staging ring, the next step's first copies issued before the result is read back"},
             "gpu_launches": (step_obj.LAUNCHES_PER_MICROBATCH * n_micro + step_obj.LAUNCHES_PER_SHARD) * args.steps,
             "launch_mode": "cuda_graph_replay" if graph is not None else "plain",
             "roofline": {"bound": "hbm", "kernel": "wigner_bwd_dg_kernel<Cfg8B> (+ wigner_reduce_partials)", "achieved": kernels[dom]["gbs"], "peak": peak,
@@ -510,6 +526,8 @@ def run_ours(args):
                                   "frac": round(value / world * 6656 / 1e9 / peak, 4)},
             "kernels": kernels,
             "loss": loss_value, "g_item_rep_norm": g_item_norm, "e2e_loss": e2e_loss,
+            # the loss is the sum of two large cancelling terms: compare runs relative to the terms, not to their difference
+            "loss_terms": {"item_rep_dot_grad": loss_term_a, "log_q_dot_g_log_q": loss_value - loss_term_a},
         }
         if not args.no_parity:
             line["parity"] = parity_block(FusedSO3ActionStep, lt, mu, sigma, eps, glq, item, gy[g_first % NBUF], dev)

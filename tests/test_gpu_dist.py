@@ -44,7 +44,7 @@ def shard_step(world, rank, dev):
         st.decode_forward(i * MICRO, (i + 1) * MICRO, item, y)
         st.decode_backward(i * MICRO, (i + 1) * MICRO, item, gy[(g_first + i) % 3], accumulate=True)
     st.latent_backward(mu, sigma, eps, glq, g_mu, g_sigma)
-    red = lvdist.pack_reduction((item * st.g_item).sum() + torch.dot(log_q, glq), st.g_item)
+    red = lvdist.pack_reduction(bench.step_loss(item, st.g_item, log_q, glq), st.g_item)
     return red, (g_mu, g_sigma, lo, hi)
 
 

@@ -704,3 +704,109 @@ def test_fused_heads_nsample_and_fallbacks(mods):
         assert not m2._fused and tuple(out.shape) == (1, 8, 3, 3) and tuple(m2.kl().shape) == (8,)
     mod.deterministic()
     assert torch.equal(mod(x)[0], mod.mu_lie)
+
+
+# ----------------------------------------------------------------------- BASELINE sizes against the oracle (row subsets)
+def test_reparam_baseline_size_subset_vs_oracle(mods):
+    """BASELINE configs[1] (B = 2^20, k = 3) through the persistent kernels: a random 8 192-row subset of z, log_q, g_mu and
+    g_sigma against the float64 oracle evaluated on exactly those rows (samples are independent)."""
+    lt, rp, _ = mods
+    torch.manual_seed(11)
+    B, S, k = 1 << 20, 8192, 3
+    mu = lt.random_group_matrices(B, device="cuda").requires_grad_(True)
+    sigma = torch.nn.functional.softplus(torch.randn(B, 3, device="cuda")).requires_grad_(True)
+    eps = torch.randn(1, B, 3, device="cuda")
+    wz, wl = torch.randn(1, B, 3, 3, device="cuda"), torch.randn(1, B, device="cuda")
+    z, lq = rp.so3_reparameterize(mu, sigma, eps, k)
+    ((z * wz).sum() + (lq * wl).sum()).backward()
+    idx = torch.randperm(B, device="cuda")[:S]
+    sub = lambda t, d=0: t.detach().index_select(d, idx).double().cpu()
+    z64, lq64, gmu64, gsg64 = oracle_reparam(sub(mu), sub(sigma), sub(eps, 1), k, sub(wz, 1), sub(wl, 1), torch.float64)
+    z32, lq32, gmu32, gsg32 = oracle_reparam(sub(mu), sub(sigma), sub(eps, 1), k, sub(wz, 1), sub(wl, 1), torch.float32)
+    close(sub(z, 1), z64, RTOL, ATOL, "z")
+    as_good_as_ref32(sub(mu.grad), gmu64, gmu32, "g_mu")
+    as_good_as_ref32(sub(lq, 1), lq64, lq32, "log_q")
+    as_good_as_ref32(sub(sigma.grad), gsg64, gsg32, "g_sigma")
+
+
+def test_action_net_baseline_size_subset_vs_oracle(mods):
+    """BASELINE configs[2] (N = 65 536, degrees 8, 10 channels) through ActionNet: a random 8 192-row subset of the output and
+    of g_angles against the float64 oracle on those rows; g_item_rep (a sum over ALL rows) against the oracle's gradient for
+    the subset plus the complement's contribution evaluated by the kernels' own transpose action in float64 accumulation."""
+    lt, _, dc = mods
+    torch.manual_seed(12)
+    N, L, C, S = 65536, 8, 10, 8192
+    M = (L + 1) ** 2
+    ang = O.group_matrix_to_eazyz(O.random_group_matrices(N, dtype=torch.float64)).float().cuda()
+    net = dc.ActionNet(L, torch.nn.Sequential(), rep_copies=C).cuda()
+    g = torch.randn(N, M * C, device="cuda")
+    a = ang.clone().requires_grad_(True)
+    out = net(a)
+    (out * g).sum().backward()
+    idx = torch.randperm(N, device="cuda")[:S]
+    a64 = ang.index_select(0, idx).double().cpu().requires_grad_(True)
+    it64 = net.item_rep.detach().double().cpu().requires_grad_(True)
+    g_sub = g.index_select(0, idx).double().cpu()
+    out64 = O.action_net_forward(a64, it64, L)
+    (out64 * g_sub).sum().backward()
+    a32 = a64.detach().float().requires_grad_(True)
+    it32 = it64.detach().float().requires_grad_(True)
+    out32 = O.action_net_forward(a32, it32, L)
+    (out32 * g_sub.float()).sum().backward()
+    as_good_as_ref32(out.detach().index_select(0, idx), out64.detach(), out32.detach(), "y")
+    as_good_as_ref32(a.grad.index_select(0, idx), a64.grad, a32.grad, "g_angles")
+    # g_item_rep: subset by the oracle + complement by sum_n D_n^T g_n (float64 accumulation of the float32 transpose action)
+    mask = torch.ones(N, dtype=torch.bool, device="cuda")
+    mask[idx] = False
+    comp = lt.block_wigner_matrix_multiply(ang[mask], g[mask].view(-1, M, C), L, transpose=True).double().sum(0).cpu()
+    want = it64.grad + comp
+    got = net.item_rep.grad.double().cpu()
+    assert (got - want).abs().max().item() <= 2e-5 * want.abs().max().item()
+
+
+@pytest.mark.parametrize("variant", ["with_mlp", "buffer_item_rep", "buffer_transpose_mlp"])
+def test_action_net_mlp_and_buffer_variants_vs_oracle(mods, variant):
+    """ActionNet(with_mlp=True) (``decoders.py:39-41,58-59``) and the fixed ``item_rep`` buffer (``decoders.py:36-37``):
+    forward and backward on the GPU against the float64 oracle action followed by the same MLP weights in float64."""
+    _, _, dc = mods
+    torch.manual_seed(21)
+    N, L, C = 777, 4, 10
+    M = (L + 1) ** 2
+    tr = variant == "buffer_transpose_mlp"
+    with_mlp = variant != "buffer_item_rep"
+    fixed = None if variant == "with_mlp" else torch.randn(M, C)
+    net = dc.ActionNet(L, torch.nn.Sequential(), rep_copies=C, with_mlp=with_mlp, item_rep=fixed, transpose=tr).cuda()
+    assert ("item_rep" in dict(net.named_buffers())) == (fixed is not None)
+    assert ("item_rep" in dict(net.named_parameters())) == (fixed is None)
+    ang64 = O.group_matrix_to_eazyz(O.random_group_matrices(N, dtype=torch.float64))
+    w = torch.randn(N, M * C, dtype=torch.float64)
+    a = ang64.float().cuda().requires_grad_(True)
+    out = net(a)
+    (out * w.float().cuda()).sum().backward()
+
+    def oracle(dtype):
+        import copy
+        a_ = ang64.detach().clone().to(dtype).requires_grad_(True)
+        it = net.item_rep.detach().cpu().clone().to(dtype).requires_grad_(fixed is None)
+        y = O.action_net_forward(a_, it, L, tr)
+        mlp = copy.deepcopy(net.mlp).cpu().to(dtype) if with_mlp else None
+        if mlp is not None:
+            y = mlp(y)
+        (y * w.to(dtype)).sum().backward()
+        grads = {"g_angles": a_.grad}
+        if fixed is None:
+            grads["g_item_rep"] = it.grad
+        if mlp is not None:
+            grads.update({"g_mlp." + k: p.grad for k, p in mlp.named_parameters()})
+        return y.detach(), grads
+    y64, g64 = oracle(torch.float64)
+    y32, g32 = oracle(torch.float32)
+    as_good_as_ref32(out, y64, y32, "out")
+    ours = {"g_angles": a.grad}
+    if fixed is None:
+        ours["g_item_rep"] = net.item_rep.grad
+    if with_mlp:
+        ours.update({"g_mlp." + k: p.grad for k, p in net.mlp.named_parameters()})
+    assert set(ours) == set(g64)
+    for k in g64:
+        as_good_as_ref32(ours[k], g64[k], g32[k], k, floor=4.0 if k.startswith("g_mlp") else 1.0)   # cuBLAS (TF32-free) sums vs CPU order

@@ -67,6 +67,21 @@ for k in (3, 10):
         z, lq = rp.so3_reparameterize(mu, sg, eps, k)
         torch.autograd.backward([z, lq], [gz, glq])
     row("configs[1] so3_reparameterize fwd+bwd, B=2^20, k=%d" % k, timed(step), B, 248)
+# the same public function captured by torch.cuda.make_graphed_callables (lie_vae_b200/graphed.py): forward and backward
+# replay as one graph launch each -- no Function.apply / engine / ctypes cost per call
+import lie_vae_b200.graphed as gr  # noqa: E402
+for k in (3, 10):
+    mu0, sg0, eps0, _, _ = sets[0]
+    g_fn = gr.graphed(lambda m, s, e, k=k: rp.so3_reparameterize(m, s, e, k),
+                      (mu0.detach().clone().requires_grad_(True), sg0.detach().clone().requires_grad_(True), eps0.clone()))
+
+    def step_g(i, g_fn=g_fn):
+        mu, sg, eps, gz, glq = sets[i % NSET]
+        mu.grad = sg.grad = None
+        z, lq = g_fn(mu, sg, eps)
+        torch.autograd.backward([z, lq], [gz, glq])
+    row("configs[1] so3_reparameterize fwd+bwd, B=2^20, k=%d, public API under make_graphed_callables" % k, timed(step_g, iters=50), B, 248)
+    del g_fn
 sg_stress = [(0.02 + 2.48 * torch.rand(B, 3, device=dev)).requires_grad_(True) for _ in range(NSET)]
 
 
@@ -124,6 +139,16 @@ for C, tr in ((10, False), (10, True), (1, False)):
         net.item_rep.grad = None
         net(a).backward(gs[i % 3])
     row("configs[2] ActionNet fwd+bwd, N=65536, l<=8, C=%d%s" % (C, ", transpose" if tr else ""), timed(step), N, 2 * 4 * M * C + 36)
+    if C == 10 and not tr:
+        g_net = gr.graphed(net, (angs[0].detach().clone().requires_grad_(True),))
+
+        def step_gn(i, g_net=g_net, net=net, gs=gs):
+            a = angs[i % 2]
+            a.grad = None
+            net.item_rep.grad = None
+            g_net(a).backward(gs[i % 3])
+        row("configs[2] ActionNet fwd+bwd, N=65536, l<=8, C=10, public API under make_graphed_callables", timed(step_gn, iters=50), N, 2 * 4 * M * C + 36)
+        del g_net
     if C == 10:
         yb, gang, gitem = torch.empty(N, M * C, device=dev), torch.empty(N, 3, device=dev), torch.empty(M, C, device=dev)
         nws = _cabi.lib().lv_wigner_bwd_workspace_floats(N, 0, L, C)
