@@ -218,6 +218,18 @@ int lv_wigner_generic_bwd_f64(const double* angles, const double* spectrum, cons
                               double* gangle_parts, double* gspectrum, int64_t N, int lmin, int lmax, int C,
                               int shared_spectrum, int transpose, void* stream);
 
+/* ---- the consumer of the Wigner action on the tensor cores: out (M, N) = A (M, K) * Bt (N, K)^T + bias.
+ *   First layer of DeconvNet, ConvTranspose2d(M*C -> hidden, 4, 1, 0) on a 1x1 input (experiments/nets.py:65-66): A = the
+ *   action output y (samples, 810), Bt = the weight (810, hidden, 4, 4) viewed (810, 16*hidden) and transposed,
+ *   bias index = column / bias_div (bias_div = 16); first Linear of ActionNet's MLP (decoders.py:39-41): bias_div = 1.
+ *   tcgen05.mma kind::tf32 (TF32 operands, FP32 accumulation in TMEM -- cuDNN's default arithmetic for the reference's FP32
+ *   convolutions), weight tiles by TMA.  A: 8-byte aligned, even lda >= K; Bt: 16-byte aligned, ldb >= K a multiple of 4
+ *   floats; out: ldo >= N; bias may be NULL.  A is rounded to TF32 (nearest) inside the kernel; Bt is read with its low 13
+ *   mantissa bits ignored -- round it once with lv_round_tf32_f32 (in place allowed) for unbiased products. ---- */
+int lv_round_tf32_f32(const float* in, float* out, int64_t n, void* stream);
+int lv_gemm_tf32_f32(const float* A, int64_t lda, const float* Bt, int64_t ldb, const float* bias, int bias_div, float* out,
+                     int64_t ldo, int64_t M, int N, int K, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

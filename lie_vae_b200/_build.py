@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblievae_sm100a.so")
-SOURCES = ["cabi.cu", "elementwise.cu", "reparam.cu", "wigner.cu", "wigner_generic.cu", "head_reparam.cu"]
+SOURCES = ["cabi.cu", "elementwise.cu", "reparam.cu", "wigner.cu", "wigner_generic.cu", "head_reparam.cu", "gemm_tf32.cu"]
 HEADERS = ["common.cuh", "wigner_gen.cuh", "wigner_bwd_dg.cuh", "reparam_core.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

@@ -536,3 +536,110 @@ def wigner_apply(angles, spectrum, lmin, lmax, transpose=False):
     if angles.dtype == torch.float32 and spectrum.dtype == torch.float32 and lmax <= FAST_MAX_DEGREE:
         return WignerApply.apply(angles, spectrum, lmin, lmax, transpose)
     return WignerApplyGeneric.apply(angles, spectrum, lmin, lmax, transpose)
+
+
+# ------------------------------------------------------------------------------ the action's consumer on the tensor cores
+def round_tf32(t):
+    """Nearest-TF32 copy of a float32 tensor (cvt.rna: what cuBLAS / cuDNN apply to TF32 operands)."""
+    dev = _require_cuda(t)
+    src = t.contiguous()
+    out = torch.empty_like(src)
+    with _on(dev):
+        _cabi.call("lv_round_tf32_f32", _cabi.ptr(src), _cabi.ptr(out), src.numel(), _stream())
+    return out
+
+
+def gemm_tf32(a, bt, bias=None, bias_div=1, out=None):
+    """out (M,N) = a (M,K) @ bt (N,K)^T + bias[col // bias_div]: tcgen05 TF32 tensor-core GEMM (lv_gemm_tf32_f32).
+    ``a`` / ``bt`` / ``out`` may be row-strided views (last dim contiguous).  ``a`` is rounded to TF32 in the kernel; pass
+    ``bt`` through ``round_tf32`` for unbiased products (its low 13 mantissa bits are otherwise ignored)."""
+    dev = _require_cuda(a, bt, bias)
+    for t in (a, bt) + ((bias,) if bias is not None else ()):
+        if t.dtype != torch.float32:
+            raise TypeError("gemm_tf32 is float32 (TF32 tensor-core arithmetic), got %s" % t.dtype)
+    if a.dim() != 2 or bt.dim() != 2 or a.shape[1] != bt.shape[1] or a.stride(1) != 1 or bt.stride(1) != 1:
+        raise ValueError("gemm_tf32: a (M,K) and bt (N,K) with contiguous rows expected, got %s %s" % (tuple(a.shape), tuple(bt.shape)))
+    M, K = a.shape
+    N = bt.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=dev)
+    elif tuple(out.shape) != (M, N) or out.stride(1) != 1 or out.dtype != torch.float32:
+        raise ValueError("gemm_tf32: out must be a float32 (M,N) view with contiguous rows")
+    with _on(dev):
+        _cabi.call("lv_gemm_tf32_f32", _cabi.ptr(a), a.stride(0), _cabi.ptr(bt), bt.stride(0), _cabi.ptr(bias), int(bias_div),
+                   _cabi.ptr(out), out.stride(0), M, N, K, _stream())
+    return out
+
+
+ACTION_GEMM_CHUNK = 8192      # samples per chunk: y of a chunk (3 240 B/sample for l <= 8, C = 10) stays L2-resident
+
+
+class ActionGemm(Function):
+    """angles (N,3), item_rep (M,C), weight (M*C, Nout), bias -> (N, Nout) = wigner_apply(angles, item_rep).view(N, M*C) @ weight + bias.
+
+    The Wigner action fused with its consumer: the first ConvTranspose2d of DeconvNet on the 1x1 input
+    (``experiments/nets.py:65-66``; weight viewed (M*C, 16*hidden), bias_div = 16) or the first Linear of ActionNet's MLP
+    (``decoders.py:39-41``; weight = linear.weight.t(), bias_div = 1).  Samples are processed in chunks whose action output y
+    stays in L2: per chunk the Wigner forward kernel writes y into a reused buffer and the tcgen05 TF32 GEMM reads it back
+    from L2; y never round-trips through HBM and is not kept for the backward, which recomputes it per chunk (forward is
+    HBM-free there too), runs dgrad / wgrad on cuBLAS and feeds g_y straight into the Wigner backward kernel.
+    """
+
+    @staticmethod
+    def forward(ctx, angles, item_rep, weight, bias, bias_div, lmax, transpose, chunk):
+        dev = _require_cuda(angles, item_rep, weight, bias)
+        if angles.dim() != 2 or angles.shape[1] != 3 or item_rep.dim() != 2:
+            raise ValueError("angles (N,3) and a shared item_rep (M,C) expected")
+        N, (Mh, C) = angles.shape[0], item_rep.shape
+        if Mh != (lmax + 1) ** 2 or tuple(weight.shape[:1]) != (Mh * C,) or weight.dim() != 2:
+            raise ValueError("weight must be (M*C = %d, Nout), got %s" % (Mh * C, tuple(weight.shape)))
+        K, Nout = weight.shape
+        a_c, s_c = angles.contiguous(), item_rep.contiguous()
+        ldb = (K + 3) // 4 * 4
+        wt = torch.zeros((Nout, ldb), dtype=torch.float32, device=dev)       # K-major weight, rows padded to 16 bytes for TMA
+        wt[:, :K] = weight.t()
+        with _on(dev):
+            _cabi.call("lv_round_tf32_f32", _cabi.ptr(wt), _cabi.ptr(wt), wt.numel(), _stream())     # nearest TF32, once per call
+        out = torch.empty((N, Nout), dtype=torch.float32, device=dev)
+        chunk = max(1, min(int(chunk), N)) if N else 1
+        ybuf = torch.empty((chunk, K), dtype=torch.float32, device=dev)
+        with _on(dev):
+            st = _stream()
+            for lo in range(0, N, chunk):
+                n = min(chunk, N - lo)
+                _cabi.call("lv_wigner_apply_fwd_f32", _cabi.ptr(a_c[lo:lo + n]), _cabi.ptr(s_c), _cabi.ptr(ybuf), n, 0, lmax, C, 1, int(bool(transpose)), st)
+                _cabi.call("lv_gemm_tf32_f32", _cabi.ptr(ybuf), K, _cabi.ptr(wt), ldb, _cabi.ptr(bias), int(bias_div), _cabi.ptr(out[lo:lo + n]),
+                           Nout, n, Nout, K, st)
+        ctx.save_for_backward(a_c, s_c, weight)
+        ctx.meta = (N, lmax, C, K, Nout, int(bias_div), bool(transpose), chunk, bias is not None)
+        ctx.set_materialize_grads(False)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        a_c, s_c, weight = ctx.saved_tensors
+        N, lmax, C, K, Nout, bias_div, transpose, chunk, has_bias = ctx.meta
+        dev = a_c.device
+        if gout is None:
+            return (None,) * 8
+        g = gout.contiguous()
+        gang = torch.empty((N, 3), dtype=torch.float32, device=dev)
+        gitem = torch.zeros_like(s_c)
+        gw = torch.zeros((K, Nout), dtype=torch.float32, device=dev)
+        ybuf = torch.empty((chunk, K), dtype=torch.float32, device=dev)
+        gybuf = torch.empty((chunk, K), dtype=torch.float32, device=dev)
+        with _on(dev):
+            st = _stream()
+            nws = _cabi.lib().lv_wigner_bwd_workspace_floats(chunk, 0, lmax, C)
+            ws = torch.empty(max(nws, 1), dtype=torch.float32, device=dev)
+            for lo in range(0, N, chunk):
+                n = min(chunk, N - lo)
+                gc = g[lo:lo + n]
+                _cabi.call("lv_wigner_apply_fwd_f32", _cabi.ptr(a_c[lo:lo + n]), _cabi.ptr(s_c), _cabi.ptr(ybuf), n, 0, lmax, C, 1, int(transpose), st)
+                gw.addmm_(ybuf[:n].t(), gc)                                  # wgrad (cuBLAS), y from L2
+                torch.matmul(gc, weight.t(), out=gybuf[:n])                 # dgrad (cuBLAS, FP32): g_y = g_out @ W^T, stays in L2
+                _cabi.call("lv_wigner_apply_bwd_f32", _cabi.ptr(a_c[lo:lo + n]), _cabi.ptr(s_c), _cabi.ptr(gybuf), _cabi.ptr(gang[lo:lo + n]),
+                           _cabi.ptr(gitem), _cabi.ptr(ws), nws, n, 0, lmax, C, 3, int(transpose), st)
+        gbias = g.view(N, Nout // bias_div, bias_div).sum((0, 2)) if has_bias else None
+        return gang, gitem, gw, gbias, None, None, None, None

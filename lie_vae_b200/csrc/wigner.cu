@@ -365,9 +365,6 @@ constexpr int WD_PL = WD_PROD_WARPS * 32;       // producer lanes
 // tile buffers in the ring: as many as shared memory holds (degrees 0..8: 4 x 51.8 KB, degrees 0..6: 6 x 31.4 KB)
 __host__ __device__ constexpr int wd_bufs(int LT) { return LT <= 6 ? 6 : 4; }
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
-}
 
 template <int CT, int LT>
 __global__ void __launch_bounds__(WD_THREADS, 1)

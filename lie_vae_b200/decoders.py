@@ -50,11 +50,43 @@ class ActionNet(nn.Module):
             self.mlp = None
 
         self.deconv = deconv
+        # fuse_consumer: run the action together with the layer that consumes it -- the first Linear of the MLP or the first
+        # ConvTranspose2d(M*C -> hidden, 4, 1, 0) of a DeconvNet-shaped ``deconv`` (experiments/nets.py:63-66) -- as chunks of
+        # [Wigner forward kernel -> tcgen05 TF32 GEMM] whose intermediate y stays in L2.  TF32 operands (what
+        # cuDNN uses for the reference's FP32 convolutions by default); off by default: the FP32-exact path is the parity path.
+        self.fuse_consumer = False
+
+    def _consumer(self):
+        """(weight (M*C, Nout), bias, bias_div, view shape after it, layers that follow, then ``deconv``?) of the layer that
+        consumes the action output, or None if its shape is not one the fused op covers."""
+        mc = self.matrix_dims * self.rep_copies
+        if self.mlp is not None:
+            lin = self.mlp[0]
+            if isinstance(lin, nn.Linear) and lin.in_features == mc:
+                return lin.weight.t(), lin.bias, 1, None, list(self.mlp)[1:], True
+            return None
+        layers = list(self.deconv) if isinstance(self.deconv, nn.Sequential) else []
+        if len(layers) >= 2 and isinstance(layers[1], nn.ConvTranspose2d) and type(layers[0]).__name__ == "View":
+            ct = layers[1]
+            if (ct.in_channels == mc and tuple(ct.kernel_size) == (4, 4) and tuple(ct.stride) == (1, 1) and tuple(ct.padding) == (0, 0)
+                    and tuple(ct.output_padding) == (0, 0) and tuple(ct.dilation) == (1, 1) and ct.groups == 1):
+                return ct.weight.reshape(mc, ct.out_channels * 16), ct.bias, 16, (ct.out_channels, 4, 4), layers[2:], False
+        return None
 
     def forward(self, angles):
         """Input is ZYZ Euler angles."""
         n, d = angles.shape
         assert d == 3, 'Input should be Euler angles.'
+        cons = self._consumer() if (self.fuse_consumer and angles.is_cuda and angles.dtype == torch.float32
+                                    and self.degrees <= _ops.FAST_MAX_DEGREE) else None
+        if cons is not None:
+            weight, bias, bias_div, shape, rest, then_deconv = cons
+            x = _ops.ActionGemm.apply(angles, self.item_rep, weight, bias, bias_div, self.degrees, self.transpose, _ops.ACTION_GEMM_CHUNK)
+            if shape is not None:
+                x = x.view(-1, *shape)
+            for layer in rest:
+                x = layer(x)
+            return self.deconv(x) if then_deconv else x
         item = _ops.wigner_apply(angles, self.item_rep, 0, self.degrees, self.transpose) \
             .view(-1, self.matrix_dims * self.rep_copies)
         if self.mlp:
