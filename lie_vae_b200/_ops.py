@@ -581,8 +581,9 @@ class ActionGemm(Function):
     (``experiments/nets.py:65-66``; weight viewed (M*C, 16*hidden), bias_div = 16) or the first Linear of ActionNet's MLP
     (``decoders.py:39-41``; weight = linear.weight.t(), bias_div = 1).  Samples are processed in chunks whose action output y
     stays in L2: per chunk the Wigner forward kernel writes y into a reused buffer and the tcgen05 TF32 GEMM reads it back
-    from L2; y never round-trips through HBM and is not kept for the backward, which recomputes it per chunk (forward is
-    HBM-free there too), runs dgrad / wgrad on cuBLAS and feeds g_y straight into the Wigner backward kernel.
+    from L2; y never round-trips through HBM and is not kept for the backward, which recomputes it per chunk, runs the
+    data gradient g_y = g_out W^T on the same tcgen05 kernel (TF32, like cuDNN's default for the reference's convolution),
+    feeds it from L2 straight into the Wigner backward kernel, and leaves the weight gradient y^T g_out to cuBLAS (FP32).
     """
 
     @staticmethod
@@ -629,6 +630,7 @@ class ActionGemm(Function):
         gw = torch.zeros((K, Nout), dtype=torch.float32, device=dev)
         ybuf = torch.empty((chunk, K), dtype=torch.float32, device=dev)
         gybuf = torch.empty((chunk, K), dtype=torch.float32, device=dev)
+        w_r = round_tf32(weight) if Nout % 4 == 0 else None
         with _on(dev):
             st = _stream()
             nws = _cabi.lib().lv_wigner_bwd_workspace_floats(chunk, 0, lmax, C)
@@ -638,7 +640,12 @@ class ActionGemm(Function):
                 gc = g[lo:lo + n]
                 _cabi.call("lv_wigner_apply_fwd_f32", _cabi.ptr(a_c[lo:lo + n]), _cabi.ptr(s_c), _cabi.ptr(ybuf), n, 0, lmax, C, 1, int(transpose), st)
                 gw.addmm_(ybuf[:n].t(), gc)                                  # wgrad (cuBLAS), y from L2
-                torch.matmul(gc, weight.t(), out=gybuf[:n])                 # dgrad (cuBLAS, FP32): g_y = g_out @ W^T, stays in L2
+                # dgrad on the tensor cores too: g_y = g_out (n, Nout) @ W^T -- W (K, Nout) is already the K-major "Bt" of this
+                # product; g_y stays in L2 for the Wigner backward
+                if w_r is not None:
+                    _cabi.call("lv_gemm_tf32_f32", _cabi.ptr(gc), Nout, _cabi.ptr(w_r), Nout, None, 1, _cabi.ptr(gybuf), K, n, K, Nout, st)
+                else:                                                       # weight rows not 16-byte aligned for TMA: cuBLAS
+                    torch.matmul(gc, weight.t(), out=gybuf[:n])
                 _cabi.call("lv_wigner_apply_bwd_f32", _cabi.ptr(a_c[lo:lo + n]), _cabi.ptr(s_c), _cabi.ptr(gybuf), _cabi.ptr(gang[lo:lo + n]),
                            _cabi.ptr(gitem), _cabi.ptr(ws), nws, n, 0, lmax, C, 3, int(transpose), st)
         gbias = g.view(N, Nout // bias_div, bias_div).sum((0, 2)) if has_bias else None

@@ -16,7 +16,7 @@
 // oracle at 2e-3 relative to the output's rms (tests/test_gpu_gemm.py); the FP32-exact path stays the default.
 //
 // Anatomy (one 128 x 128 output tile per CTA, K in blocks of 32 floats = one 128-byte swizzle row, 4-stage ring):
-//   warps 0-3  A producers: row t of the tile, 8-byte cp.async pieces placed in the SWIZZLE_128B K-major layout by hand (rows
+//   warps 0-3  A producers: 8-byte cp.async pieces (a warp covers two whole row segments) placed in the SWIZZLE_128B K-major layout by hand (rows
 //              of y are 3 240 B apart -- 8-byte, not 16-byte aligned, so TMA cannot address them), zero-filled past M and K;
 //              thread 0 also issues the TMA load of the 128 x 32 weight tile (CU_TENSOR_MAP_SWIZZLE_128B, OOB rows/cols = 0).
 //              After the main loop the same warps are the epilogue: tcgen05.ld 32 lanes x 32 columns, + bias, 128-bit stores.
@@ -80,10 +80,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_b, const float* __restri
 
     if (warp < 4) {
         // ------------------------------------------------------------ A producers (+ thread 0: TMA of the weight tile)
-        const int row = tid, grow = m0 + row;
-        const bool valid = grow < M;
-        const float* arow = A + int64_t(valid ? grow : 0) * lda;
-        const uint32_t swz = uint32_t(row & 7);
+        // Piece (i, tid): 8 bytes of row i*8 + tid/16 at byte offset (tid%16)*8 -- a warp instruction covers two whole 128-byte row
+        // segments (coalesced), and the same thread later rounds exactly the pieces it copied (no hand-over between threads).
+        const int prow = tid >> 4, pcol = tid & 15;
+        const uint32_t poff = uint32_t(pcol & 1) * 8u;
         for (int kb = 0; kb < nkb + GT_LOOKAHEAD; ++kb) {
             if (kb < nkb) {
                 const int s = kb % GT_STAGES;
@@ -94,40 +94,42 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_b, const float* __restri
                                  :: "r"(smem_u32(sB + s * GT_TILE_BYTES)), "l"(reinterpret_cast<uint64_t>(&tm_b)), "r"(kb * GT_BK), "r"(n0),
                                     "r"(smem_u32(full + s)) : "memory");
                 }
-                const uint32_t drow = smem_u32(sA + s * GT_TILE_BYTES) + uint32_t(row) * 128u;
-                const int k0 = kb * GT_BK;
+                const uint32_t dtile = smem_u32(sA + s * GT_TILE_BYTES);
+                const int kk = kb * GT_BK + 2 * pcol;
 #pragma unroll
-                for (int p = 0; p < 16; ++p) {                     // 8-byte pieces; 16-byte chunk c = p / 2 lands at chunk c ^ (row & 7)
-                    const int kk = k0 + 2 * p;
-                    int nbytes = valid ? (K - kk) * 4 : 0;
+                for (int i = 0; i < 16; ++i) {
+                    const int r = i * 8 + prow, gr = m0 + r;
+                    int nbytes = gr < M ? (K - kk) * 4 : 0;
                     nbytes = nbytes < 0 ? 0 : (nbytes > 8 ? 8 : nbytes);
-                    const uint32_t dst = drow + ((uint32_t(p >> 1) ^ swz) << 4) + uint32_t(p & 1) * 8u;
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(arow + (nbytes > 0 ? kk : 0)), "r"(nbytes) : "memory");
+                    // 16-byte chunk c = pcol / 2 of row r lands at chunk c ^ (r & 7) (SWIZZLE_128B)
+                    const uint32_t dst = dtile + uint32_t(r) * 128u + ((uint32_t(pcol >> 1) ^ uint32_t(r & 7)) << 4) + poff;
+                    const float* src = A + (nbytes > 0 ? int64_t(gr) * lda + kk : 0);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
                 }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
             if (kb >= GT_LOOKAHEAD) {
-                asm volatile("cp.async.wait_group %0;" ::"n"(GT_LOOKAHEAD) : "memory");      // the pieces of block kb - LOOKAHEAD have landed
+                asm volatile("cp.async.wait_group %0;" ::"n"(GT_LOOKAHEAD) : "memory");      // this thread's pieces of block kb - LOOKAHEAD have landed
                 // The tensor core reads FP32 words and ignores the low 13 mantissa bits (truncation: every product shrinks by
-                // 2^-11 on average).  Round this row's 32 operands to TF32 (nearest, ties away: cvt.rna) in place, as cuBLAS /
-                // cuDNN do before their TF32 MMAs; chunk order rotated by the row so that a quarter-warp hits 8 different
-                // bank groups.  (The weight tile arrives by TMA: the caller rounds Bt once, lv_round_tf32_f32.)
-                const uint32_t rrow = smem_u32(sA + ((kb - GT_LOOKAHEAD) % GT_STAGES) * GT_TILE_BYTES) + uint32_t(row) * 128u;
+                // 2^-11 on average).  Round the operands to TF32 (nearest, ties away: cvt.rna) in place, as cuBLAS / cuDNN do
+                // before their TF32 MMAs.  (The weight tile arrives by TMA: the caller rounds Bt once, lv_round_tf32_f32.)
+                const uint32_t rtile = smem_u32(sA + ((kb - GT_LOOKAHEAD) % GT_STAGES) * GT_TILE_BYTES);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const uint32_t addr = rrow + (((uint32_t(i) + swz) & 7u) << 4);
-                    uint32_t x0, x1, x2, x3;
-                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "r"(addr));
+                for (int i = 0; i < 16; ++i) {
+                    const int r = i * 8 + prow;
+                    const uint32_t addr = rtile + uint32_t(r) * 128u + ((uint32_t(pcol >> 1) ^ uint32_t(r & 7)) << 4) + poff;
+                    uint32_t x0, x1;
+                    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(x0), "=r"(x1) : "r"(addr));
                     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(x0) : "f"(__uint_as_float(x0)));
                     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(x1) : "f"(__uint_as_float(x1)));
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(x2) : "f"(__uint_as_float(x2)));
-                    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(x3) : "f"(__uint_as_float(x3)));
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x0), "r"(x1), "r"(x2), "r"(x3) : "memory");
+                    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(x0), "r"(x1) : "memory");
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                  // generic-proxy writes -> visible to the tensor core
                 mbar_arrive(full + (kb - GT_LOOKAHEAD) % GT_STAGES);
             }
         }
+        const int row = tid, grow = m0 + row;                // epilogue: thread t owns accumulator row (TMEM lane) t
+        const bool valid = grow < M;
         // ------------------------------------------------------------ epilogue: TMEM -> registers -> + bias -> global
         mbar_wait(tmem_full, 0);
         tc_fence_after();

@@ -58,8 +58,8 @@ def test_gemm_tf32_vs_float64(mods, M, N, K):
                                                    (8, 384, 16, 20001, False, 8192)])
 def test_action_gemm_function_vs_float64(mods, L, Nout, div, N, tr, chunk):
     """ActionGemm (chunked Wigner forward -> tcgen05 GEMM; backward: recompute, cuBLAS dgrad / wgrad, Wigner backward) against
-    float64 autograd of oracle-action @ weight + bias.  The function is linear in weight / bias / item_rep and the backward
-    never sees the TF32-rounded forward, so the gradients are held to FP32 accuracy, only the output to TF32 accuracy."""
+    float64 autograd of oracle-action @ weight + bias.  The output and the gradients that flow through the data-gradient GEMM
+    (g_angles, g_item_rep) are TF32-accurate; the weight / bias gradients (cuBLAS FP32 on the recomputed y) FP32-accurate."""
     _ops, _ = mods
     torch.manual_seed(L + Nout)
     C = 10
@@ -76,8 +76,9 @@ def test_action_gemm_function_vs_float64(mods, L, Nout, div, N, tr, chunk):
     out = _ops.ActionGemm.apply(a, it, w, b, div, L, tr, chunk)
     (out * gw.float().cuda()).sum().backward()
     assert rel_rms(out, out64.detach()) < TF32_TOL
-    for got, want, what in ((a.grad, ang64.grad, "g_angles"), (it.grad, it64.grad, "g_item_rep"), (w.grad, w64.grad, "g_weight"), (b.grad, b64.grad, "g_bias")):
-        assert rel_rms(got, want) < 1e-4, what
+    for got, want, what, tol in ((a.grad, ang64.grad, "g_angles", TF32_TOL), (it.grad, it64.grad, "g_item_rep", TF32_TOL),
+                                 (w.grad, w64.grad, "g_weight", 1e-4), (b.grad, b64.grad, "g_bias", 1e-4)):
+        assert rel_rms(got, want) < tol, what
 
 
 @pytest.mark.parametrize("kind,L,hidden,N", [("deconv", 8, 50, 1000), ("deconv", 6, 200, 1024), ("mlp", 4, 0, 777)])
