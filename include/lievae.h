@@ -201,6 +201,12 @@ int lv_wigner_apply_bwd_f32(const float* angles, const float* spectrum, const fl
                             float* gspectrum, float* workspace, int64_t workspace_floats, int64_t N, int lmin,
                             int lmax, int C, int shared_spectrum, int transpose, void* stream);
 
+/* ---- the action fused with the reconstruction term of VAE.log_likelihood (experiments/vae.py:164-171, 199-204; toy deconv):
+ *   out (N) = sum_{m,c} (D(angles_i) item_rep - x[i % B])^2 for the (n, B)-flat sample index i; the action output itself is
+ *   never written.  x (B, M, C).  Forward only (the IWAE bound is an evaluation metric). ---- */
+int lv_wigner_recon_sse_f32(const float* angles, const float* item_rep, const float* x, float* out, int64_t N, int64_t B,
+                            int lmin, int lmax, int C, int transpose, void* stream);
+
 /* ---- the same action for ANY degree range (lmax <= lv_wigner_generic_max_degree()) and for float64: run-time loops over
  *   a caller-owned dense J table `jtable` = J_0 | J_1 | ... | J_lmax (row-major (2l+1)^2 blocks, block l at offset
  *   l(2l-1)(2l+1)/3; lie_tools.j_matrix lie_tools.py:10-14).  Covers what the unrolled kernels above do not

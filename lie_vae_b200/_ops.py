@@ -528,6 +528,24 @@ class WignerApplyGeneric(Function):
         return parts.sum(1), (gspec.sum(0) if shared else gspec), None, None, None
 
 
+def wigner_recon_sse(angles, item_rep, x, lmax, transpose=False):
+    """(N) sums of squares between the action output D(angles_i) item_rep and x[i % B] (x: (B, M, C)) -- the reconstruction
+    term of ``VAE.log_likelihood`` for the toy deconv, with y never written.  No gradient (evaluation path)."""
+    dev = _require_cuda(angles, item_rep, x)
+    for t in (angles, item_rep, x):
+        if t.dtype != torch.float32:
+            raise TypeError("wigner_recon_sse is float32 only, got %s" % t.dtype)
+    M, C = item_rep.shape
+    if angles.dim() != 2 or angles.shape[1] != 3 or M != (lmax + 1) ** 2 or x.dim() != 3 or tuple(x.shape[1:]) != (M, C):
+        raise ValueError("angles (N,3), item_rep ((lmax+1)^2, C) and x (B, M, C) expected")
+    N, B = angles.shape[0], x.shape[0]
+    out = torch.empty(N, dtype=torch.float32, device=dev)
+    with _on(dev):
+        _cabi.call("lv_wigner_recon_sse_f32", _cabi.ptr(angles.detach().contiguous()), _cabi.ptr(item_rep.detach().contiguous()),
+                   _cabi.ptr(x.detach().contiguous()), _cabi.ptr(out), N, B, 0, int(lmax), C, int(bool(transpose)), _stream())
+    return out
+
+
 FAST_MAX_DEGREE = 8   # degrees covered by the unrolled, packed float32 kernels
 
 

@@ -243,6 +243,46 @@ wigner_fwd_kernel(const float* __restrict__ angles, const float* __restrict__ sp
     }
 }
 
+// ------------------------------------------------------------------ forward fused with the reconstruction term
+// VAE.log_likelihood (experiments/vae.py:164-171; n = 500 importance samples of one datapoint) needs only
+// log p(x|z) = -sum_{m,c} (y - x)^2 of the decoded harmonics (VAE.recon_loss, vae.py:199-204, with the toy deconv): the
+// action output y (n*B, M, C) is reduced against x (B, M, C) inside the kernel and never written.  Sample i belongs to
+// datapoint i % B (the (n, B) layout of the reference).  Run-time C and degree range; forward only (evaluation path).
+__global__ void __launch_bounds__(WG_MAX_THREADS, 1)
+wigner_sse_kernel(const float* __restrict__ angles, const float* __restrict__ spectrum, const float* __restrict__ x, float* __restrict__ out,
+                  int64_t N, int64_t B, int lmin, int lmax, int C, int S, int transpose) {
+    extern __shared__ __align__(16) float smem[];
+    const int M = (lmax + 1) * (lmax + 1) - lmin * lmin;
+    const int MC = M * C;
+    float* tile = smem;
+    float* s_trig = smem + align4i(S * MC);
+    float* s_part = s_trig + S * WG_TRIG_STRIDE;        // [S * C] per-column sums of squares
+    const int64_t n0 = int64_t(blockIdx.x) * S;
+    const int rows = int(min(int64_t(S), N - n0));
+    stage_trig(s_trig, angles, n0, rows, transpose);
+    __syncthreads();
+    const int t = threadIdx.x;
+    const int s = t / C, c = t - s * C;
+    if (s < rows) {
+        const float4* tg = reinterpret_cast<const float4*>(s_trig + s * WG_TRIG_STRIDE);
+        float* trow = tile + s * MC + c;
+        fwd_degrees<-1, true>(spectrum + c, trow, C, tg, lmin, lmax);
+        const float* xrow = x + ((n0 + s) % B) * MC + c;
+        float acc = 0.f;
+        for (int m = 0; m < M; ++m) {
+            const float d = trow[m * C] - __ldg(xrow + m * C);
+            acc = fmaf(d, d, acc);
+        }
+        s_part[t] = acc;
+    }
+    __syncthreads();
+    if (t < rows) {
+        float a = 0.f;
+        for (int cc = 0; cc < C; ++cc) a += s_part[t * C + cc];
+        out[n0 + t] = a;
+    }
+}
+
 // ------------------------------------------------------------------ backward
 // Persistent CTAs over sample tiles.  workspace (SHARED only): [gridDim.x][MC] partial sums.
 template <bool SHARED, int CT, int LT>
@@ -738,6 +778,20 @@ extern "C" int lv_wigner_apply_fwd_f32(const float* angles, const float* spectru
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (shared_spectrum) return WG_DISPATCH(C, lmin, lmax, true, lv::launch_fwd, g, angles, spectrum, out, N, lmin, lmax, C, transpose, st);
     return WG_DISPATCH(C, lmin, lmax, false, lv::launch_fwd, g, angles, spectrum, out, N, lmin, lmax, C, transpose, st);
+}
+
+extern "C" int lv_wigner_recon_sse_f32(const float* angles, const float* item_rep, const float* x, float* out, int64_t N, int64_t B,
+                                       int lmin, int lmax, int C, int transpose, void* stream) {
+    lv::WgGeom g;
+    int rc = lv::wigner_geometry("wigner_recon_sse", N, lmin, lmax, C, true, g);
+    if (rc) return rc;
+    if (N == 0) return LV_OK;
+    if (B <= 0 || !angles || !item_rep || !x || !out) { lv::set_error("wigner_recon_sse: null pointer or empty batch"); return LV_ERR_ARG; }
+    const size_t smem = size_t(lv::align4i(g.S * g.MC) + g.S * lv::WG_TRIG_STRIDE + g.S * C) * 4;
+    rc = lv::opt_in_smem(lv::wigner_sse_kernel, smem);
+    if (rc) return rc;
+    lv::wigner_sse_kernel<<<unsigned(g.ntiles), g.threads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(angles, item_rep, x, out, N, B, lmin, lmax, C, g.S, transpose);
+    return lv::check_launch("wigner_recon_sse");
 }
 
 extern "C" int lv_wigner_apply_bwd_f32(const float* angles, const float* spectrum, const float* gout, float* gangles,

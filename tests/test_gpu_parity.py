@@ -306,3 +306,39 @@ def test_iwae_log_likelihood_path(lt):
     log_p_z = torch.full((n, B), rp.LOG_PRIOR_SO3, dtype=torch.float64, device="cuda")
     got = ut.iwae_log_likelihood(log_p_x_z, log_p_z, lqc)
     assert abs(got.item() - ref.item()) < 5e-4 * max(1.0, abs(ref.item())), (got.item(), ref.item())
+
+
+@pytest.mark.parametrize("n,B,L,C", [(500, 1, 8, 10), (500, 1, 4, 3), (7, 33, 6, 10), (3, 1000, 2, 1)])
+def test_iwae_fused_reconstruction(lt, n, B, L, C):
+    """The reconstruction term of VAE.log_likelihood fused into the Wigner forward (lv_wigner_recon_sse_f32): per-sample
+    sum_{m,c} (D item_rep - x[i % B])^2 against the float64 oracle, and ``utils.action_log_likelihood`` (sampler -> Euler ->
+    fused action + SSE -> log-sum-exp over n) against the oracle's IWAE bound on the same noise."""
+    import lie_vae_b200.reparameterize as rp
+    import lie_vae_b200.decoders as dc
+    import lie_vae_b200.utils as ut
+    from lie_vae_b200 import _ops
+    torch.manual_seed(n + B + L)
+    M = (L + 1) ** 2
+    ang64 = O.group_matrix_to_eazyz(O.random_group_matrices(n * B, dtype=torch.float64))
+    item64, x64 = torch.randn(M, C, dtype=torch.float64), torch.randn(B, M, C, dtype=torch.float64)
+    y64 = O.action_net_forward(ang64, item64, L).reshape(n, B, M, C)
+    want = ((y64 - x64) ** 2).sum((-1, -2)).reshape(-1)
+    got = _ops.wigner_recon_sse(ang64.float().cuda(), item64.float().cuda(), x64.float().cuda(), L)
+    close(got, want, 2e-5, 2e-5 * float(want.abs().max()), "sse")
+    # the whole evaluation path from encoder features, fixed noise
+    k = 10
+    rep = rp.SO3reparameterize(rp.N0reparameterize(10, 3), rp.AlgebraMean(10), k=k).cuda()
+    net = dc.ActionNet(L, torch.nn.Sequential(), rep_copies=C).cuda()
+    net.item_rep.data = item64.float().cuda()
+    feats = torch.randn(B, 10, device="cuda")
+    eps = torch.randn(n, B, 3, device="cuda")
+    rep.reparameterize.sample_noise = lambda n_=1, like=None: eps
+    got_ll = ut.action_log_likelihood(rep, net, feats, x64.float().cuda(), n)
+    with torch.no_grad():
+        mu64 = O.rodrigues(rep.mean_module.map(feats).double().cpu())
+        sg64 = torch.nn.functional.softplus(rep.reparameterize.sigma_linear(feats)).double().cpu()
+    z, lq = O.so3_reparameterize(mu64, sg64, eps.double().cpu(), k)
+    rec = O.action_net_forward(O.group_matrix_to_eazyz(z.reshape(-1, 3, 3)), item64, L).reshape(n, B, M, C)
+    w = -((rec - x64) ** 2).sum((-1, -2)) + O.so3_log_prior(z) - lq
+    ref = (O.logsumexp(w, 0) - math.log(n)).mean()
+    assert abs(got_ll.item() - ref.item()) < 1e-3 * max(1.0, abs(ref.item())), (got_ll.item(), ref.item())
