@@ -443,7 +443,7 @@ def run_ours(args):
             m = stage[b][0].requires_grad_(True)
             s = stage[b][1].requires_grad_(True)
             ang3, lq = rp.so3_reparameterize_philox(m, s, 1, K_WIND, PHILOX_SEED, lo + i * e_micro, euler=True)
-            yy = _ops.WignerApply.apply(ang3[0], item_p, 0, L_MAX, False)
+            yy = _ops.wigner_apply(ang3[0], item_p, 0, L_MAX, False)
             # the decoder that would consume y is outside the hot path: its gradient g_y (and g_log_q) is handed
             # to autograd directly, exactly as a downstream module's backward would
             glq_i = glq[i * e_micro:(i + 1) * e_micro]

@@ -50,7 +50,7 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed compiling %s" % src)
         if verbose:
             sys.stderr.write("==== %s\n%s" % (src, log))
-    link = [_nvcc(), "-shared", "-o", LIB] + [j[1] for j in jobs]
+    link = [_nvcc(), "-shared", "-Xlinker", "-soname=" + os.path.basename(LIB), "-o", LIB] + [j[1] for j in jobs]
     proc = subprocess.run(link, cwd=CSRC, capture_output=True, text=True)
     if proc.returncode != 0:
         sys.stderr.write(proc.stdout[-4000:] + proc.stderr[-8000:])
@@ -58,5 +58,34 @@ def build(force=False, verbose=False):
     return LIB
 
 
+TORCH_EXT_NAME = "lievae_torch"
+TORCH_EXT_DIR = os.path.join(HERE, "build_torch")
+TORCH_EXT_LIB = os.path.join(TORCH_EXT_DIR, TORCH_EXT_NAME + ".so")
+TORCH_EXT_SRC = os.path.join(CSRC, "torch_binding.cpp")
+
+
+def torch_ext_is_stale():
+    if not os.path.exists(TORCH_EXT_LIB):
+        return True
+    t = os.path.getmtime(TORCH_EXT_LIB)
+    return os.path.getmtime(TORCH_EXT_SRC) > t or os.path.getmtime(os.path.join(os.path.dirname(HERE), "include", "lievae.h")) > t
+
+
+def build_torch_ext(force=False, verbose=False):
+    """Compile csrc/torch_binding.cpp (C++ autograd Functions over the C ABI; host code only, no device code) in-tree with
+    torch.utils.cpp_extension; linked against liblievae_sm100a.so next to it (rpath $ORIGIN/..)."""
+    if not force and not torch_ext_is_stale():
+        return TORCH_EXT_LIB
+    build()
+    from torch.utils import cpp_extension
+    os.makedirs(TORCH_EXT_DIR, exist_ok=True)
+    cpp_extension.load(name=TORCH_EXT_NAME, sources=[TORCH_EXT_SRC], extra_cflags=["-O2", "-std=c++17"],
+                       extra_ldflags=["-L" + HERE, "-l:" + os.path.basename(LIB), "-Wl,-rpath,'$$ORIGIN/..'"],    # $$ for ninja, quotes for sh
+                       build_directory=TORCH_EXT_DIR, with_cuda=True, verbose=verbose)
+    return TORCH_EXT_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--no-torch-ext" not in sys.argv:
+        print(build_torch_ext(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -36,7 +36,14 @@ class HotPath(nn.Module):
 
 
 def graphed(fn_or_module, sample_args, num_warmup_iters=3):
-    """``torch.cuda.make_graphed_callables`` with this package's conventions (sample tensors on the module's device)."""
+    """``torch.cuda.make_graphed_callables`` with this package's conventions (sample tensors on the module's device).
+
+    Garbage is collected first: a CUDA graph (or any cached block) that Python frees *during* a capture makes the allocator
+    call ``cudaFree``, which is illegal while a stream is capturing and invalidates the capture (seen when one graphed
+    callable is dropped and the next one captured right after)."""
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
     return torch.cuda.make_graphed_callables(fn_or_module, tuple(sample_args), num_warmup_iters=num_warmup_iters)
 
 

@@ -32,7 +32,7 @@ def so3_reparameterize(mu, sigma, eps, k=10):
     Returns z = mu @ exp(hat(eps*sigma)) of shape (n,B,3,3) and log q(z|x) of shape (n,B).
     Differentiable in mu and sigma.
     """
-    return _ops.SO3Reparam.apply(mu, sigma, eps, k)
+    return _ops.so3_reparam(mu, sigma, eps, k, False)
 
 
 def so3_reparameterize_eazyz(mu, sigma, eps, k=10):
@@ -42,7 +42,7 @@ def so3_reparameterize_eazyz(mu, sigma, eps, k=10):
     decoder (``experiments/vae.py:182``) -- and log q (n,B); the 3x3 pose never leaves registers.
     Differentiable in mu and sigma.
     """
-    return _ops.SO3ReparamEazyz.apply(mu, sigma, eps, k)
+    return _ops.so3_reparam(mu, sigma, eps, k, True)
 
 
 def so3_reparameterize_philox(mu, sigma, n=1, k=10, seed=0, offset=0, euler=False):

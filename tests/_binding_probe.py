@@ -60,6 +60,11 @@ def main():
     assert vae_mod.SO3reparameterize is lie_vae_b200.reparameterize.SO3reparameterize
     assert vae_mod.ActionNet is lie_vae_b200.decoders.ActionNet
     assert vae_mod.group_matrix_to_eazyz is lie_vae_b200.lie_tools.group_matrix_to_eazyz
+    # the regularisers (losses/*.py) are callers of lie_tools only: unedited, they pick up the kernels too
+    import lie_vae.losses.equivariance_loss as eq
+    import lie_vae.losses.encoder_continuity_loss as ec
+    assert eq.__file__.startswith(refshim.REFERENCE_ROOT) and eq.s2s1rodrigues is lie_vae_b200.lie_tools.s2s1rodrigues
+    assert ec.EncoderContinuityLoss(None, lamb=2.0)(torch.arange(12.0).view(4, 3), 0).item() == 2.0 * 27.0
     models = build_all(VAE)
     ref_sd = torch.load(sys.argv[2])
     report = {}
