@@ -143,6 +143,14 @@ struct Cfg8B {      // 14 math warps + 2 producer warps; group loads per warp 64
     using G3 = DegList<5, 3>;     static constexpr int W3 = 3;
     using G4 = DegList<4, 2>;     static constexpr int W4 = 2;
 };
+struct Cfg8C {      // 14 math + 2 producer warps, the partition a cost model fitted to Cfg8B's measured loop lengths ranks best
+    static constexpr int LT = 8, NG = 5, PROD = 2, S = 12, NB = 5;
+    using G0 = DegList<8>;        static constexpr int W0 = 3;
+    using G1 = DegList<7>;        static constexpr int W1 = 3;
+    using G2 = DegList<6, 1>;     static constexpr int W2 = 3;
+    using G3 = DegList<4, 3, 2>;  static constexpr int W3 = 3;
+    using G4 = DegList<5, 0>;     static constexpr int W4 = 2;
+};
 struct Cfg8A6 : Cfg8A { static constexpr int S = 6, NB = 10; };     // the same with 6-sample tiles: a finer-grained ring
 struct Cfg8B6 : Cfg8B { static constexpr int S = 6, NB = 10; };
 struct Cfg8B18 : Cfg8B { static constexpr int S = 18, NB = 3; };    // 18-sample tiles: a producer warp's 27 jobs fill one pass
@@ -155,10 +163,11 @@ struct Cfg6A {      // degrees 0..6 (BASELINE configs[3]): 14 math warps + 2 pro
     using G4 = DegList<>;         static constexpr int W4 = 0;
 };
 
-// measured (2^20 samples per launch, one B200): Cfg8B 0.676-0.694 ms, Cfg8B18 0.706, Cfg8A 0.869 (one producer warp cannot keep
-// up: 36 jobs = two passes per tile), 6-sample tiles 1.22-1.28 (per-tile producer work dominates); first TMA-fed kernel 0.740
+// measured (2^20 samples per launch, one B200): Cfg8C 0.688 ms next to Cfg8B 0.695 on the same box (0.676-0.694 over boxes),
+// Cfg8B18 0.706, Cfg8A 0.869 (one producer warp cannot keep up: 36 jobs = two passes per tile), 6-sample tiles 1.22-1.28
+// (per-tile producer work dominates); first TMA-fed kernel 0.740
 #ifndef LV_DG_CFG8
-#define LV_DG_CFG8 Cfg8B
+#define LV_DG_CFG8 Cfg8C
 #endif
 
 constexpr int DG_C = 10, DG_SL = 3;          // channels; samples per slice (30 lanes)
