@@ -384,10 +384,16 @@ def run_ours(args):
     loss_term_a = float((item.double().view(-1) * red[1:].double()).sum())
     # per-kernel durations: a separate, un-timed pass of plain launches bracketed by CUDA events on the launching stream
     step_obj.enable_kernel_timing(True)
+    plain = []
     for _ in range(2):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
         local_step()
+        b.record()
+        plain.append((a, b))
     torch.cuda.synchronize()
     kern_ms = {k: [a.elapsed_time(b) for a, b in v] for k, v in step_obj.events.items()}
+    plain_step_ms = min(a.elapsed_time(b) for a, b in plain)
     step_obj.enable_kernel_timing(False)
 
     # ---- end to end through the public autograd API, inputs in pinned host memory ------------------
@@ -525,6 +531,10 @@ def run_ours(args):
             "pipeline_roofline": {"bytes_per_sample": 6656, "achieved_gbs": round(value / world * 6656 / 1e9, 1),
                                   "frac": round(value / world * 6656 / 1e9 / peak, 4)},
             "kernels": kernels,
+            # where a step's time goes: the four kernels' launches, summed; one rank-local step of plain launches with event
+            # records between the kernels; the timed (graph-replayed, back-to-back) step
+            "step_breakdown_ms": {"sum_of_kernel_launches": round(sum(sum(v) / len(v) * (n_micro if k.startswith("wigner") else 1) for k, v in kern_ms.items()), 3),
+                                  "local_step_plain_launches": round(plain_step_ms, 3), "timed_step": round(ms_per_step, 3)},
             "loss": loss_value, "g_item_rep_norm": g_item_norm, "e2e_loss": e2e_loss,
             # the loss is the sum of two large cancelling terms: compare runs relative to the terms, not to their difference
             "loss_terms": {"item_rep_dot_grad": loss_term_a, "log_q_dot_g_log_q": loss_value - loss_term_a},

@@ -7,7 +7,6 @@ FP32 ConvTranspose2d by default.  ``-m gpu``.
 """
 import pytest
 import torch
-import torch.nn.functional as F
 
 from oracle import so3_oracle as O
 
