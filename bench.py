@@ -281,6 +281,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- this arm has no CPU fallback (use --impl reference for the CPU baseline)")
+    affinity0 = os.sched_getaffinity(0)
     cpus_bound = bind_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -542,6 +543,7 @@ def run_ours(args):
         if not args.no_parity:
             line["parity"] = parity_block(FusedSO3ActionStep, lt, mu, sigma, eps, glq, item, gy[g_first % NBUF], dev)
         if not args.no_cpu_baseline and world == 1:
+            os.sched_setaffinity(0, affinity0)          # the CPU baseline gets every host core again
             threads = os.cpu_count() or 1
             sample = CPU_SAMPLE
             times = cpu_reference_run(sample, 3, 1, threads)
