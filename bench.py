@@ -526,7 +526,7 @@ def run_ours(args):
                            "generated in the kernel; 4-deep staging ring, the next step's first copies issued before the result is read back"},
             "gpu_launches": (step_obj.LAUNCHES_PER_MICROBATCH * n_micro + step_obj.LAUNCHES_PER_SHARD) * args.steps,
             "launch_mode": "cuda_graph_replay" if graph is not None else "plain",
-            "roofline": {"bound": "hbm", "kernel": "wigner_bwd_dg_kernel<Cfg8C> (+ wigner_reduce_partials)", "achieved": kernels[dom]["gbs"], "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "wigner_bwd_dg_kernel<Cfg8BP> (+ wigner_reduce_partials)", "achieved": kernels[dom]["gbs"], "peak": peak,
                          "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": abytes[dom] * micro},
             "pipeline_roofline": {"bytes_per_sample": 6656, "achieved_gbs": round(value / world * 6656 / 1e9, 1),

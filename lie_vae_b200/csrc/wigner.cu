@@ -815,7 +815,7 @@ extern "C" int lv_wigner_apply_bwd_f32(const float* angles, const float* spectru
     int grid = 0;
     if (shared_spectrum && lv::dg_bwd_eligible(C, lmin, lmax, gout, N)) {
         if (lmax == 8) return lv::launch_bwd_dg<lv::dg::LV_DG_CFG8>(g, angles, spectrum, gout, gangles, gspectrum, workspace, workspace_floats, N, transpose, accumulate, st);
-        return lv::launch_bwd_dg<lv::dg::Cfg6A>(g, angles, spectrum, gout, gangles, gspectrum, workspace, workspace_floats, N, transpose, accumulate, st);
+        return lv::launch_bwd_dg<lv::dg::LV_DG_CFG6>(g, angles, spectrum, gout, gangles, gspectrum, workspace, workspace_floats, N, transpose, accumulate, st);
     }
     if (shared_spectrum && lv::ws_bwd_eligible(C, lmin, lmax, gout, N)) {
         if (lmax == 8) return lv::launch_bwd_ws<8>(g, angles, spectrum, gout, gangles, gspectrum, workspace, workspace_floats, N, transpose, accumulate, st);

@@ -128,7 +128,7 @@ template <int L, int... R> struct GroupMap<DegList<L, R...>> {
 // work per column and degree (instructions: loads + 3 pair rotations + 2 J multiplies + 3 dots + accumulate):
 //   l = 8: 191, 7: 179, 6: 169, 5: 124, 4: 83, 3: 75, 2: 69, 1: 36, 0: 2
 struct Cfg8A {      // 15 math warps + 1 producer warp; group loads 191 / 179 / 171 / 193 / 194
-    static constexpr int LT = 8, NG = 5, PROD = 1, S = 12, NB = 5;
+    static constexpr int LT = 8, NG = 5, PROD = 1, S = 12, NB = 5, SPI = 1;
     using G0 = DegList<8>;        static constexpr int W0 = 3;
     using G1 = DegList<7>;        static constexpr int W1 = 3;
     using G2 = DegList<6, 0>;     static constexpr int W2 = 3;
@@ -136,7 +136,7 @@ struct Cfg8A {      // 15 math warps + 1 producer warp; group loads 191 / 179 / 
     using G4 = DegList<4, 3, 1>;  static constexpr int W4 = 3;
 };
 struct Cfg8B {      // 14 math warps + 2 producer warps; group loads per warp 64 / 60 / 68 / 66 / 76
-    static constexpr int LT = 8, NG = 5, PROD = 2, S = 12, NB = 5;
+    static constexpr int LT = 8, NG = 5, PROD = 2, S = 12, NB = 5, SPI = 1;
     using G0 = DegList<8, 0>;     static constexpr int W0 = 3;
     using G1 = DegList<7>;        static constexpr int W1 = 3;
     using G2 = DegList<6, 1>;     static constexpr int W2 = 3;
@@ -144,18 +144,23 @@ struct Cfg8B {      // 14 math warps + 2 producer warps; group loads per warp 64
     using G4 = DegList<4, 2>;     static constexpr int W4 = 2;
 };
 struct Cfg8C {      // 14 math + 2 producer warps, the partition a cost model fitted to Cfg8B's measured loop lengths ranks best
-    static constexpr int LT = 8, NG = 5, PROD = 2, S = 12, NB = 5;
+    static constexpr int LT = 8, NG = 5, PROD = 2, S = 12, NB = 5, SPI = 1;
     using G0 = DegList<8>;        static constexpr int W0 = 3;
     using G1 = DegList<7>;        static constexpr int W1 = 3;
     using G2 = DegList<6, 1>;     static constexpr int W2 = 3;
     using G3 = DegList<4, 3, 2>;  static constexpr int W3 = 3;
     using G4 = DegList<5, 0>;     static constexpr int W4 = 2;
 };
+struct Cfg8CP : Cfg8C { static constexpr int SPI = 2; };            // two slices per item
+struct Cfg8BP : Cfg8B { static constexpr int SPI = 2; };
+struct Cfg8BQ : Cfg8B { static constexpr int SPI = 4; };            // a whole 12-sample tile per item
+struct Cfg8B18P : Cfg8B { static constexpr int S = 18, NB = 3, SPI = 2; };
+struct Cfg8B18T : Cfg8B { static constexpr int S = 18, NB = 3, SPI = 3; };
 struct Cfg8A6 : Cfg8A { static constexpr int S = 6, NB = 10; };     // the same with 6-sample tiles: a finer-grained ring
 struct Cfg8B6 : Cfg8B { static constexpr int S = 6, NB = 10; };
 struct Cfg8B18 : Cfg8B { static constexpr int S = 18, NB = 3; };    // 18-sample tiles: a producer warp's 27 jobs fill one pass
 struct Cfg6A {      // degrees 0..6 (BASELINE configs[3]): 14 math warps + 2 producer warps; loads per warp 42 / 40.5 / 39.5 / 34.5
-    static constexpr int LT = 6, NG = 4, PROD = 2, S = 12, NB = 8;
+    static constexpr int LT = 6, NG = 4, PROD = 2, S = 12, NB = 8, SPI = 1;
     using G0 = DegList<6>;        static constexpr int W0 = 4;
     using G1 = DegList<5, 1, 0>;  static constexpr int W1 = 4;
     using G2 = DegList<4, 3>;     static constexpr int W2 = 4;
@@ -163,11 +168,16 @@ struct Cfg6A {      // degrees 0..6 (BASELINE configs[3]): 14 math warps + 2 pro
     using G4 = DegList<>;         static constexpr int W4 = 0;
 };
 
-// measured (2^20 samples per launch, one B200): Cfg8C 0.688 ms next to Cfg8B 0.695 on the same box (0.676-0.694 over boxes),
-// Cfg8B18 0.706, Cfg8A 0.869 (one producer warp cannot keep up: 36 jobs = two passes per tile), 6-sample tiles 1.22-1.28
-// (per-tile producer work dominates); first TMA-fed kernel 0.740
+// measured (2^20 samples per launch, one B200, same box): Cfg8BP 0.638 ms (two slices per item, no lane-divergent code in the
+// loop), Cfg8B18T 0.643, Cfg8CP 0.661 (the {4,3,2} group spills), Cfg8B18P 0.723, Cfg8BQ 0.741 (one item per tile: too coarse);
+// with one slice per item: Cfg8C 0.685-0.688, Cfg8B 0.676-0.695, Cfg8B18 0.706, Cfg8A 0.869 (one producer warp cannot keep up:
+// 36 jobs = two passes per tile), 6-sample tiles 1.22-1.28 (per-tile producer work dominates); first TMA-fed kernel 0.740
 #ifndef LV_DG_CFG8
-#define LV_DG_CFG8 Cfg8C
+#define LV_DG_CFG8 Cfg8BP
+#endif
+struct Cfg6AP : Cfg6A { static constexpr int SPI = 2; };
+#ifndef LV_DG_CFG6
+#define LV_DG_CFG6 Cfg6AP
 #endif
 
 constexpr int DG_C = 10, DG_SL = 3;          // channels; samples per slice (30 lanes)
@@ -175,6 +185,7 @@ constexpr int DG_C = 10, DG_SL = 3;          // channels; samples per slice (30 
 template <class CFG> struct Geo {
     static constexpr int M = (CFG::LT + 1) * (CFG::LT + 1), MC = M * DG_C;
     static constexpr int SLICES = CFG::S / DG_SL;
+    static constexpr int SPI = CFG::SPI;                        // slices per work item
     static constexpr int MATH = CFG::W0 + CFG::W1 + CFG::W2 + CFG::W3 + CFG::W4;
     static constexpr int WARPS = MATH + CFG::PROD, THREADS = WARPS * 32;
     static constexpr uint32_t TILE_BYTES = CFG::S * MC * 4u;
@@ -185,7 +196,7 @@ template <class CFG> struct Geo {
     static constexpr int RED_STRIDE = 24;                       // elements per warp in the final reduction buffer (>= max group elems)
     static constexpr size_t SMEM = size_t(CFG::NB) * TILE_FLOATS * 4 + size_t(CFG::NB) * CFG::S * WG_TRIG_STRIDE * 4 + 2 * CFG::NB * 8 +
                                    size_t(CFG::PROD) * PASSES * 32 * 4 + 16;
-    static_assert(CFG::S % DG_SL == 0 && CFG::S % CFG::PROD == 0 && (CFG::S * MC) % 4 == 0, "tile geometry");
+    static_assert(CFG::S % DG_SL == 0 && CFG::S % CFG::PROD == 0 && (CFG::S * MC) % 4 == 0 && SLICES % SPI == 0, "tile geometry");
     static_assert(WARPS == 16, "16 warps x 128 registers fill the register file");
     static_assert(GroupInfo<typename CFG::G0>::elems <= RED_STRIDE && GroupInfo<typename CFG::G1>::elems <= RED_STRIDE &&
                   GroupInfo<typename CFG::G2>::elems <= RED_STRIDE && GroupInfo<typename CFG::G3>::elems <= RED_STRIDE &&
@@ -198,24 +209,29 @@ template <class CFG> struct Geo {
 // ---------------------------------------------------------------------------------------------------------- math warps
 template <class CFG, class GL, int W>
 __device__ __forceinline__ void math_group(int wg, int red_warp, const float* __restrict__ spectrum, float* tiles, const float* trig_all,
-                                           uint64_t* full, uint64_t* empty, int my_tiles, int ragged_q, int last_rows, float* red) {
+                                           uint64_t* full, uint64_t* empty, int my_tiles, float* red) {
     using G = Geo<CFG>;
     constexpr int C = DG_C, MC = G::MC, SLOT = GroupInfo<GL>::first * GroupInfo<GL>::first;
     static_assert(GroupInfo<GL>::first >= 1, "the group's first degree provides the three T_k slots");
     const int lane = threadIdx.x & 31;
-    const bool active = lane < 30;
-    const int la = active ? lane : 29;            // lanes 30, 31 shadow lane 29 (no divergence), their results are dropped
+    const int la = lane < 30 ? lane : 29;         // lanes 30, 31 shadow lane 29 (no divergence), their results are dropped
     const int sl = la / C, c = la - sl * C;
     GroupState<GL> st;
     group_init<C>(st, spectrum + c);
+    // an item = SPI consecutive 3-sample slices of one tile: one full-barrier wait, one release and one round of bookkeeping per
+    // item (SPI = 2: ~20 instructions less per slice and half the barrier traffic)
+    constexpr int SPI = G::SPI, IPT = G::SLICES / SPI;
     int q = 0, p = wg, buf = 0;
     uint32_t par = 0;
-    while (p >= G::SLICES) { p -= G::SLICES; ++q; if (++buf == CFG::NB) { buf = 0; par ^= 1u; } }
+    while (p >= IPT) { p -= IPT; ++q; if (++buf == CFG::NB) { buf = 0; par ^= 1u; } }
+    // No lane-divergent code in the loop: lanes 30 / 31 recompute lane 29's column (same addresses, same values; their
+    // accumulators are never read), and the rows a ragged last tile does not have are zero-filled by the producer (zero g_y
+    // contributes zero to every sum), so no sample-validity test is needed here.
     while (q < my_tiles) {
         mbar_wait(full + buf, par);
-        const int rows = q == ragged_q ? last_rows : CFG::S;
-        const int s = p * DG_SL + sl;
-        if (active && s < rows) {
+#pragma unroll 1
+        for (int h = 0; h < SPI; ++h) {
+            const int s = (p * SPI + h) * DG_SL + sl;
             float* col = tiles + buf * G::TILE_FLOATS + s * MC + c;
             TAcc t;
             group_run<C>(st, col, reinterpret_cast<const float4*>(trig_all + (buf * CFG::S + s) * WG_TRIG_STRIDE), t);
@@ -227,7 +243,7 @@ __device__ __forceinline__ void math_group(int wg, int red_warp, const float* __
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + buf);       // release: slot writes visible to the producer
         p += W;
-        while (p >= G::SLICES) { p -= G::SLICES; ++q; if (++buf == CFG::NB) { buf = 0; par ^= 1u; } }
+        while (p >= IPT) { p -= IPT; ++q; if (++buf == CFG::NB) { buf = 0; par ^= 1u; } }
     }
     named_bar_sync(3, G::THREADS);                     // every tile consumed, every T slot read: the ring is free
     group_flush(st, red + red_warp * G::RED_STRIDE * 32 + lane);
@@ -252,14 +268,14 @@ wigner_bwd_dg_kernel(const float* __restrict__ angles, const float* __restrict__
     // CTA-local index of the (possibly ragged) last tile of the launch, -1 if another CTA owns it
     const int ragged_q = (my_tiles > 0 && first + int64_t(my_tiles - 1) * stride == ntiles - 1 && last_rows < S) ? my_tiles - 1 : -1;
     if (tid == 0) {
-        for (int b = 0; b < NB; ++b) { mbar_init(full + b, 1 + PROD); mbar_init(empty + b, CFG::NG * G::SLICES); }
+        for (int b = 0; b < NB; ++b) { mbar_init(full + b, 1 + PROD); mbar_init(empty + b, CFG::NG * (G::SLICES / G::SPI)); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     float* red = tiles;                                               // final reduction buffer [MATH][RED_STRIDE][32] (reuses the ring)
 
     constexpr int B1 = CFG::W0, B2 = B1 + CFG::W1, B3 = B2 + CFG::W2, B4 = B3 + CFG::W3, B5 = B4 + CFG::W4;
-#define DG_ARGS spectrum, tiles, trig_all, full, empty, my_tiles, ragged_q, last_rows, red
+#define DG_ARGS spectrum, tiles, trig_all, full, empty, my_tiles, red
     if (warp < B1) {
         math_group<CFG, typename CFG::G0, CFG::W0>(warp, warp, DG_ARGS);
     } else if (warp < B2) {
@@ -315,6 +331,12 @@ wigner_bwd_dg_kernel(const float* __restrict__ angles, const float* __restrict__
                 for (int i = 0; i < 4; ++i) d[i] = make_float4(tr[4 * i], tr[4 * i + 1], tr[4 * i + 2], tr[4 * i + 3]);
             }
         };
+        auto zero_tail = [&](int j) {       // every producer lane: rows a ragged tile does not have become zeros (before the arrive on full)
+            if (j == ragged_q) {
+                float* tail = tiles + (j % NB) * G::TILE_FLOATS + last_rows * MC;
+                for (int i = pw * 32 + lane; i < (S - last_rows) * MC; i += PROD * 32) tail[i] = 0.f;
+            }
+        };
         auto issue_load = [&](int j) {      // one lane: first arrival on full + the bulk load; L2 prefetch of the tile after it
             const int buf = j % NB;
             const uint32_t bytes = uint32_t(tile_rows(j)) * uint32_t(MC) * 4u;
@@ -339,6 +361,7 @@ wigner_bwd_dg_kernel(const float* __restrict__ angles, const float* __restrict__
         fetch_phi(0);
         for (int j = 0; j < NB && j < my_tiles; ++j) {
             if (pw == 0 && lane == 0) issue_load(j);
+            zero_tail(j);
             read_phi(j, phi);
             fetch_phi(j + 1);
             trig_tile(j);
@@ -382,6 +405,7 @@ wigner_bwd_dg_kernel(const float* __restrict__ angles, const float* __restrict__
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy accesses of the buffer before the bulk write
                 if constexpr (PROD > 1) named_bar_sync(1, PROD * 32); else __syncwarp();
                 if (pw == 0 && lane == 0) issue_load(jn);
+                zero_tail(jn);
                 read_phi(jn, phi);
                 fetch_phi(jn + 1);
                 trig_tile(buf);
