@@ -156,6 +156,26 @@ struct Cfg8BP : Cfg8B { static constexpr int SPI = 2; };
 struct Cfg8BQ : Cfg8B { static constexpr int SPI = 4; };            // a whole 12-sample tile per item
 struct Cfg8B18P : Cfg8B { static constexpr int S = 18, NB = 3, SPI = 2; };
 struct Cfg8B18T : Cfg8B { static constexpr int S = 18, NB = 3, SPI = 3; };
+// Measured at 2^20 samples (ms): Cfg8BP 0.637, Cfg8E 0.637, Cfg8F 0.717, Cfg8CP 0.661, Cfg8BQ 0.741, Cfg8B18P 0.723, Cfg8B18T 0.643.
+// Timing-only ablations (-DLV_DG_ABL=1: producers skip the T sums and angle gradients, =2: math warps skip the chain):
+// 0.630 and 0.494 ms -- the TMA feed alone streams at 6.9 TB/s and the producers are not the limiter; the kernel sits on the
+// FMA pipe (ncu: fma pipe 65 % active, fmaheavy 62 %, math_pipe_throttle ~ long_scoreboard) at 0.82 of the HBM copy peak.
+struct Cfg8E {      // 14 math + 2 producer warps, partition ranked best by the cost model with two slices per item
+    static constexpr int LT = 8, NG = 5, PROD = 2, S = 12, NB = 5, SPI = 2;
+    using G0 = DegList<8>;        static constexpr int W0 = 3;
+    using G1 = DegList<7>;        static constexpr int W1 = 3;
+    using G2 = DegList<6, 1, 0>;  static constexpr int W2 = 3;
+    using G3 = DegList<5, 4>;     static constexpr int W3 = 3;
+    using G4 = DegList<3, 2>;     static constexpr int W4 = 2;
+};
+struct Cfg8F {      // 13 math + 3 producer warps
+    static constexpr int LT = 8, NG = 5, PROD = 3, S = 12, NB = 5, SPI = 2;
+    using G0 = DegList<8>;        static constexpr int W0 = 3;
+    using G1 = DegList<7, 1>;     static constexpr int W1 = 3;
+    using G2 = DegList<6, 2>;     static constexpr int W2 = 3;
+    using G3 = DegList<4, 3>;     static constexpr int W3 = 2;
+    using G4 = DegList<5, 0>;     static constexpr int W4 = 2;
+};
 struct Cfg8A6 : Cfg8A { static constexpr int S = 6, NB = 10; };     // the same with 6-sample tiles: a finer-grained ring
 struct Cfg8B6 : Cfg8B { static constexpr int S = 6, NB = 10; };
 struct Cfg8B18 : Cfg8B { static constexpr int S = 18, NB = 3; };    // 18-sample tiles: a producer warp's 27 jobs fill one pass
@@ -229,12 +249,16 @@ __device__ __forceinline__ void math_group(int wg, int red_warp, const float* __
     // contributes zero to every sum), so no sample-validity test is needed here.
     while (q < my_tiles) {
         mbar_wait(full + buf, par);
-#pragma unroll 1
+#pragma unroll 1          // unrolling the item loop doubles the live state and spills: 1.24 ms
         for (int h = 0; h < SPI; ++h) {
             const int s = (p * SPI + h) * DG_SL + sl;
             float* col = tiles + buf * G::TILE_FLOATS + s * MC + c;
             TAcc t;
+#if defined(LV_DG_ABL) && (LV_DG_ABL & 2)
+            t.sx = col[0];
+#else
             group_run<C>(st, col, reinterpret_cast<const float4*>(trig_all + (buf * CFG::S + s) * WG_TRIG_STRIDE), t);
+#endif
             // T_k partials of this (group, column) into three slots of the tile this lane has consumed itself
             col[(SLOT + 0) * C] = t.sx + (wg2::plo(t.px) + wg2::phi(t.px));
             col[(SLOT + 1) * C] = t.sy + (wg2::plo(t.py) + wg2::phi(t.py));
@@ -383,7 +407,11 @@ wigner_bwd_dg_kernel(const float* __restrict__ angles, const float* __restrict__
 #pragma unroll
             for (int k = 0; k < PASSES; ++k) {
                 float a0[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, a1[5] = {0.f, 0.f, 0.f, 0.f, 0.f};     // one chain per group: short dependency chains
+#if defined(LV_DG_ABL) && (LV_DG_ABL & 1)
+                if (false) {
+#else
                 if (job_on[k] && job_s[k] < rows) {
+#endif
                     const float* base = tile + job_s[k] * MC + job_a[k] * C;
                     constexpr int slots[5] = {GroupInfo<typename CFG::G0>::first, GroupInfo<typename CFG::G1>::first, GroupInfo<typename CFG::G2>::first,
                                               GroupInfo<typename CFG::G3>::first, CFG::W4 > 0 ? GroupInfo<typename CFG::G4>::first : 0};
