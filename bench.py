@@ -383,10 +383,12 @@ def run_ours(args):
     loss_value = float(red[0])
     g_item_norm = float(red[1:].double().norm())
     loss_term_a = float((item.double().view(-1) * red[1:].double()).sum())
-    # per-kernel durations: a separate, un-timed pass of plain launches bracketed by CUDA events on the launching stream
+    # per-kernel durations: a second pass of as many steps as the timed region, plain launches bracketed by CUDA events on the
+    # launching stream, started right after it (same sustained clock / power state: under sw_power_cap a short burst runs ~7 %
+    # faster than the sustained loop and would overstate the roofline fraction)
     step_obj.enable_kernel_timing(True)
     plain = []
-    for _ in range(2):
+    for _ in range(max(2, args.steps)):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         local_step()
@@ -394,7 +396,7 @@ def run_ours(args):
         plain.append((a, b))
     torch.cuda.synchronize()
     kern_ms = {k: [a.elapsed_time(b) for a, b in v] for k, v in step_obj.events.items()}
-    plain_step_ms = min(a.elapsed_time(b) for a, b in plain)
+    plain_step_ms = sum(a.elapsed_time(b) for a, b in plain) / len(plain)
     step_obj.enable_kernel_timing(False)
 
     # ---- end to end through the public autograd API, inputs in pinned host memory ------------------

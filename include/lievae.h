@@ -93,6 +93,14 @@ int lv_vector_to_eazyz_fwd_f64(const double* v, double* e, int64_t n, void* stre
 int lv_vector_to_eazyz_bwd_f32(const float* v, const float* ge, float* gv, int64_t n, void* stream);
 int lv_vector_to_eazyz_bwd_f64(const double* v, const double* ge, double* gv, int64_t n, void* stream);
 
+/* ---- SO(2)-subgroup equivariance distance of EquivarianceLoss.forward, losses/equivariance_loss.py:27-36:
+ *      diff[i] = || Rx(theta[i]) R[i] - R2[i] ||_F^2, Rx = s2s1rodrigues(e_x, (cos, sin)); resid = Rx R - R2 is kept for the
+ *      backward, which returns gR = 2 gdiff Rx^T resid and gR2 = -2 gdiff resid (theta is a random draw: no gradient) ---- */
+int lv_equivariance_sqdist_fwd_f32(const float* theta /*n*/, const float* R /*n,9*/, const float* R2 /*n,9*/, float* diff /*n*/, float* resid /*n,9*/, int64_t n, void* stream);
+int lv_equivariance_sqdist_fwd_f64(const double* theta, const double* R, const double* R2, double* diff, double* resid, int64_t n, void* stream);
+int lv_equivariance_sqdist_bwd_f32(const float* theta, const float* resid, const float* gdiff /*n*/, float* gR, float* gR2, int64_t n, void* stream);
+int lv_equivariance_sqdist_bwd_f64(const double* theta, const double* resid, const double* gdiff, double* gR, double* gR2, int64_t n, void* stream);
+
 /* ---- out[j] = sum_i in[i*inner + j]: reduces per-sample gradients over the n axis ---- */
 int lv_sum_leading_f32(const float* in, float* out, int64_t n, int64_t inner, void* stream);
 int lv_sum_leading_f64(const double* in, double* out, int64_t n, int64_t inner, void* stream);

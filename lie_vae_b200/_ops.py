@@ -591,6 +591,45 @@ def wigner_recon_sse(angles, item_rep, x, lmax, transpose=False):
     return out
 
 
+class EquivarianceSqDist(Function):
+    """theta (n), R (n,3,3), R2 (n,3,3) -> (n) squared Frobenius distances || Rx(theta) R - R2 ||^2, Rx the rotation about the x
+    axis built as ``s2s1rodrigues(e_x, (cos, sin))`` -- the SO(3) part of ``EquivarianceLoss.forward``
+    (``losses/equivariance_loss.py:27-36``) in one kernel per direction; gradients w.r.t. R and R2."""
+
+    @staticmethod
+    def forward(ctx, theta, R, R2):
+        dev = _require_cuda(theta, R, R2)
+        sfx = _sfx(R)
+        if theta.dtype != R.dtype or R2.dtype != R.dtype:
+            raise TypeError("equivariance_sqdist: mixed dtypes")
+        if tuple(R.shape[-2:]) != (3, 3) or R2.shape != R.shape or theta.shape != R.shape[:-2]:
+            raise ValueError("equivariance_sqdist: theta (n), R (n,3,3), R2 (n,3,3) expected, got %s %s %s"
+                             % (tuple(theta.shape), tuple(R.shape), tuple(R2.shape)))
+        th, a, b = theta.reshape(-1).contiguous(), _rows(R, 9), _rows(R2, 9)
+        n = th.shape[0]
+        diff = torch.empty(n, dtype=R.dtype, device=dev)
+        resid = torch.empty((n, 9), dtype=R.dtype, device=dev)
+        with _on(dev):
+            _cabi.call("lv_equivariance_sqdist_fwd_%s" % sfx, _cabi.ptr(th), _cabi.ptr(a), _cabi.ptr(b), _cabi.ptr(diff), _cabi.ptr(resid), n, _stream())
+        ctx.save_for_backward(th, resid)
+        ctx.meta = (sfx, n, R.shape)
+        ctx.set_materialize_grads(False)
+        return diff.reshape(theta.shape)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gdiff):
+        if gdiff is None:
+            return None, None, None
+        sfx, n, shape = ctx.meta
+        th, resid = ctx.saved_tensors
+        g = gdiff.reshape(-1).contiguous()
+        gR, gR2 = torch.empty_like(resid), torch.empty_like(resid)
+        with _on(g.device):
+            _cabi.call("lv_equivariance_sqdist_bwd_%s" % sfx, _cabi.ptr(th), _cabi.ptr(resid), _cabi.ptr(g), _cabi.ptr(gR), _cabi.ptr(gR2), n, _stream())
+        return None, gR.reshape(shape), gR2.reshape(shape)
+
+
 FAST_MAX_DEGREE = 8   # degrees covered by the unrolled, packed float32 kernels
 
 

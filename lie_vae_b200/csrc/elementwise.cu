@@ -278,6 +278,51 @@ template <typename T> struct VecToEazyzBwd {
     }
 };
 
+// ------------------------------------------------------------------ SO(2)-subgroup equivariance distance
+// EquivarianceLoss.forward, losses/equivariance_loss.py:27-36: g = s2s1rodrigues(e_x, (cos th, sin th)) (the rotation by th about
+// the x axis), enc_rot = g . R, diff = || enc_rot - R2 ||_F^2 with R the encoding of an image and R2 the encoding of the image
+// rotated by th.  One thread per sample; the residual d = g R - R2 is written next to diff for the backward:
+//   g_R = 2 g_diff g^T d,   g_R2 = -2 g_diff d      (th is a random draw: no gradient).
+template <typename T>
+__device__ __forceinline__ void x_rotation(T th, T (&g)[9]) {
+    T sn, cs;
+    Sc<T>::sincos(th, &sn, &cs);
+    const T ex[3] = {T(1), T(0), T(0)};
+    axis_angle_matrix(ex, sn, T(1) - cs, g);          // exactly the arithmetic of s2s1rodrigues on (e_x, (cos, sin))
+}
+template <typename T> struct EquivSqDistFwd {
+    static constexpr int I0 = 1, I1 = 9, I2 = 9, O0 = 1, O1 = 9;
+    static __device__ __forceinline__ void run(const T* th, const T* R, const T* R2, T* diff, T* d) {
+        T g[9];
+        x_rotation(th[0], g);
+        T acc = T(0);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const T e = Sc<T>::fma(g[r * 3], R[c], Sc<T>::fma(g[r * 3 + 1], R[3 + c], g[r * 3 + 2] * R[6 + c])) - R2[r * 3 + c];
+                d[r * 3 + c] = e;
+                acc = Sc<T>::fma(e, e, acc);
+            }
+        diff[0] = acc;
+    }
+};
+template <typename T> struct EquivSqDistBwd {
+    static constexpr int I0 = 1, I1 = 9, I2 = 1, O0 = 9, O1 = 9;
+    static __device__ __forceinline__ void run(const T* th, const T* d, const T* gdiff, T* gR, T* gR2) {
+        T g[9];
+        x_rotation(th[0], g);
+        const T k = T(2) * gdiff[0];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                gR[r * 3 + c] = k * Sc<T>::fma(g[r], d[c], Sc<T>::fma(g[3 + r], d[3 + c], g[6 + r] * d[6 + c]));
+                gR2[r * 3 + c] = -k * d[r * 3 + c];
+            }
+    }
+};
+
 // ------------------------------------------------------------------ leading-axis sum (grad reduction over n)
 template <typename T>
 __global__ void sum_leading_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t n, int64_t inner) {
@@ -392,6 +437,8 @@ LV_BINARY(s2s2_gram_schmidt_fwd, S2S2Fwd)
 LV_TERNARY2(s2s2_gram_schmidt_bwd, S2S2Bwd)
 LV_UNARY(vector_to_eazyz_fwd, VecToEazyzFwd)
 LV_BINARY(vector_to_eazyz_bwd, VecToEazyzBwd)
+LV_TERNARY2(equivariance_sqdist_fwd, EquivSqDistFwd)
+LV_TERNARY2(equivariance_sqdist_bwd, EquivSqDistBwd)
 
 template <typename T>
 static int sum_leading(const T* in, T* out, int64_t n, int64_t inner, void* st) {

@@ -69,6 +69,15 @@ def s2s1rodrigues(s2_el, s1_el):
     return eye + s * K + (1.0 - c) * (K @ K)
 
 
+def equivariance_sqdist(theta, encoding, encoding_of_rotated):
+    """The SO(3) part of EquivarianceLoss.forward, losses/equivariance_loss.py:27-36: g = s2s1rodrigues(e_x, (cos, sin)),
+    enc_rot = g.bmm(encoding), diffs = (enc_rot - img_rot_enc).pow(2).view(n, -1).sum(-1).  (n),(n,3,3),(n,3,3)->(n)."""
+    n = theta.shape[0]
+    ex = torch.tensor([1.0, 0.0, 0.0], dtype=encoding.dtype, device=encoding.device).unsqueeze(0).expand(n, 3)
+    g = s2s1rodrigues(ex, torch.stack((torch.cos(theta), torch.sin(theta)), 1))
+    return (g.bmm(encoding) - encoding_of_rotated).pow(2).reshape(n, -1).sum(-1)
+
+
 def s2s2_gram_schmidt(v1, v2):
     """lie_tools.py:81-89: rows e1, e2, e1 x e2; norms clamped at 1e-5.  (N,3),(N,3)->(N,3,3).
 
