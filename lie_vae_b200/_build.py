@@ -64,11 +64,23 @@ TORCH_EXT_LIB = os.path.join(TORCH_EXT_DIR, TORCH_EXT_NAME + ".so")
 TORCH_EXT_SRC = os.path.join(CSRC, "torch_binding.cpp")
 
 
+def _torch_ext_src_hash():
+    import hashlib
+    h = hashlib.sha256()
+    for path in (TORCH_EXT_SRC, os.path.join(os.path.dirname(HERE), "include", "lievae.h")):
+        with open(path, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def torch_ext_is_stale():
-    if not os.path.exists(TORCH_EXT_LIB):
+    """True unless the built extension carries the hash of the sources it was compiled from (content, not mtimes: a snapshot
+    or checkout of the tree may reset those)."""
+    try:
+        with open(TORCH_EXT_LIB + ".srchash") as f:
+            return not os.path.exists(TORCH_EXT_LIB) or f.read().strip() != _torch_ext_src_hash()
+    except OSError:
         return True
-    t = os.path.getmtime(TORCH_EXT_LIB)
-    return os.path.getmtime(TORCH_EXT_SRC) > t or os.path.getmtime(os.path.join(os.path.dirname(HERE), "include", "lievae.h")) > t
 
 
 def build_torch_ext(force=False, verbose=False):
@@ -82,6 +94,8 @@ def build_torch_ext(force=False, verbose=False):
     cpp_extension.load(name=TORCH_EXT_NAME, sources=[TORCH_EXT_SRC], extra_cflags=["-O2", "-std=c++17"],
                        extra_ldflags=["-L" + HERE, "-l:" + os.path.basename(LIB), "-Wl,-rpath,'$$ORIGIN/..'"],    # $$ for ninja, quotes for sh
                        build_directory=TORCH_EXT_DIR, with_cuda=True, verbose=verbose)
+    with open(TORCH_EXT_LIB + ".srchash", "w") as f:
+        f.write(_torch_ext_src_hash())
     return TORCH_EXT_LIB
 
 

@@ -196,8 +196,26 @@ struct Cfg6A {      // degrees 0..6 (BASELINE configs[3]): 14 math warps + 2 pro
 #define LV_DG_CFG8 Cfg8BP
 #endif
 struct Cfg6AP : Cfg6A { static constexpr int SPI = 2; };
+struct Cfg6B {      // degrees 0..6 with a third producer warp: per sample the producers' work is what it is for degrees 0..8 while the
+    // math is 56 % of it, so two producer warps bound the kernel (Cfg6AP 0.528 ms per 2^20 samples)
+    static constexpr int LT = 6, NG = 4, PROD = 3, S = 12, NB = 8, SPI = 2;
+    using G0 = DegList<6>;        static constexpr int W0 = 4;
+    using G1 = DegList<5>;        static constexpr int W1 = 3;
+    using G2 = DegList<4, 1, 0>;  static constexpr int W2 = 3;
+    using G3 = DegList<3, 2>;     static constexpr int W3 = 3;
+    using G4 = DegList<>;         static constexpr int W4 = 0;
+};
+struct Cfg6C : Cfg6A { static constexpr int S = 18, NB = 5, SPI = 3; };     // larger tiles: the per-tile producer chain is amortised over 18 samples
+struct Cfg6D : Cfg6A { static constexpr int S = 18, NB = 5, SPI = 2; };
+struct Cfg6E : Cfg6B { static constexpr int S = 24, NB = 4, SPI = 2; };
+struct Cfg6F : Cfg6A { static constexpr int S = 24, NB = 4, SPI = 2; };
+struct Cfg6G : Cfg6B { static constexpr int S = 18, NB = 5, SPI = 2; };
+struct Cfg6H : Cfg6B { static constexpr int S = 30, NB = 3, SPI = 2; };
+// degrees 0..6, ms per 2^20 samples: Cfg6AP 0.527, Cfg6B 0.524 (a third producer warp does not help: the per-TILE chain of the
+// producers -- wait, T sums, fence, TMA issue -- is what bounds it; with the math removed 0.423), 18-sample tiles Cfg6D 0.412 /
+// Cfg6C 0.421 / Cfg6G 0.420, 24-sample Cfg6E 0.408 / Cfg6F 0.461, 30-sample Cfg6H 0.405.  Cfg6D = 0.77 of the HBM copy peak.
 #ifndef LV_DG_CFG6
-#define LV_DG_CFG6 Cfg6AP
+#define LV_DG_CFG6 Cfg6D
 #endif
 
 constexpr int DG_C = 10, DG_SL = 3;          // channels; samples per slice (30 lanes)
