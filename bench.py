@@ -13,7 +13,9 @@ resident), followed by the only collective: an NCCL all-reduce of [loss, grad it
 Prints ONE JSON line (rank 0).  `value` = samples/s with inputs resident in HBM; `e2e` = the same
 pipeline through the public autograd API with mu/sigma in pinned HOST memory (the noise is generated
 in the kernel, as the reference's module draws it itself), copies in the timed region; `roofline` =
-the dominant kernel (Wigner backward) against the measured HBM copy peak; `cpu_baseline` = the oracle
+the dominant kernel (Wigner backward) against the measured HBM copy peak, its duration taken from CUDA
+events around every launch INSIDE the timed region (plain launches; `--graph` replays a CUDA graph
+instead, same throughput) with the kernel-alone burst figure beside it; `cpu_baseline` = the oracle
 port of the reference on this box's host cores, bounded sample; `ref_cuda_eager` = the same port as
 eager PyTorch on cuda:0 (the reference's own execution model on this box); `parity` = a 4 096-sample
 slice of the step against the FP64 oracle.
@@ -332,10 +334,13 @@ def run_ours(args):
         # not depend on how the batch is cut into ranks beyond the rounding of grad item_rep itself.
         lvdist.pack_reduction(step_loss(item, g_item, log_q, glq), g_item, out=red)
 
-    # The rank-local part of a step is a fixed sequence of launches on caller-owned buffers: capture it once in a CUDA
-    # graph and replay it (no per-launch CPU cost, no gaps between the kernels); the one collective stays outside.
+    # The rank-local part of a step is a fixed sequence of launches on caller-owned buffers.  Default: plain launches with a
+    # CUDA event on either side of each of the four kernels, so that the per-kernel durations of the roofline block are
+    # measured INSIDE the timed region (sustained clocks; the host runs far ahead of the GPU at these kernel sizes).  --graph
+    # captures the sequence once and replays it (same throughput, measured; the per-kernel durations then come from a second,
+    # un-timed pass of plain launches).  The one collective stays outside either way.
     graph = None
-    if not args.no_graph:
+    if args.graph:
         try:
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream())
@@ -367,37 +372,63 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        one_step()
-    barrier()
+    # the clock sampler is a subprocess: start it BEFORE the warm-up steps, so that spawning it does not leave the GPU idle (and
+    # its clocks ramping back up) between the warm-up and the timed region
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for _ in range(args.steps):
+    for _ in range(args.warmup):
         one_step()
+    barrier()
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps - 1)]     # between the steps: where the time goes
+    live_events = graph is None
+    if live_events:
+        step_obj.enable_kernel_timing(True)
+    t0.record()
+    for i in range(args.steps):
+        one_step()
+        if i < args.steps - 1:
+            marks[i].record()
     t1.record()
     barrier()
     elapsed_ms = t0.elapsed_time(t1)
+    edges = [t0] + marks + [t1]
+    per_step_ms = [round(a.elapsed_time(b), 3) for a, b in zip(edges[:-1], edges[1:])]
     loss_value = float(red[0])
     g_item_norm = float(red[1:].double().norm())
     loss_term_a = float((item.double().view(-1) * red[1:].double()).sum())
-    # per-kernel durations: a second pass of as many steps as the timed region, plain launches bracketed by CUDA events on the
-    # launching stream, started right after it (same sustained clock / power state: under sw_power_cap a short burst runs ~7 %
-    # faster than the sustained loop and would overstate the roofline fraction)
-    step_obj.enable_kernel_timing(True)
-    plain = []
-    for _ in range(max(2, args.steps)):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        local_step()
-        b.record()
-        plain.append((a, b))
-    torch.cuda.synchronize()
-    kern_ms = {k: [a.elapsed_time(b) for a, b in v] for k, v in step_obj.events.items()}
-    plain_step_ms = sum(a.elapsed_time(b) for a, b in plain) / len(plain)
+    if live_events:
+        torch.cuda.synchronize()
+        kern_ms = {k: [a.elapsed_time(b) for a, b in v] for k, v in step_obj.events.items()}
+        plain_step_ms = None
+    else:
+        # graph replay: per-kernel durations from a second pass of as many steps, plain launches bracketed by CUDA events
+        step_obj.enable_kernel_timing(True)
+        plain = []
+        for _ in range(max(2, args.steps)):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            local_step()
+            b.record()
+            plain.append((a, b))
+        torch.cuda.synchronize()
+        kern_ms = {k: [a.elapsed_time(b) for a, b in v] for k, v in step_obj.events.items()}
+        plain_step_ms = sum(a.elapsed_time(b) for a, b in plain) / len(plain)
     step_obj.enable_kernel_timing(False)
+    # the dominant kernel timed alone (burst: a short idle, then 8 back-to-back launches): what it does outside a power-capped
+    # sustained step; reported next to the in-step figure, never instead of it
+    torch.cuda.synchronize()
+    time.sleep(0.25)
+    ba, bb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_burst = 8
+    step_obj.decode_backward(0, micro, item, gy[0], accumulate=True)
+    ba.record()
+    for j in range(n_burst):
+        step_obj.decode_backward(0, micro, item, gy[j % NBUF], accumulate=True)
+    bb.record()
+    torch.cuda.synchronize()
+    alone_ms = ba.elapsed_time(bb) / n_burst
 
     # ---- end to end through the public autograd API, inputs in pinned host memory ------------------
     # What a caller of the module hands over per sample is mu (36 B) and sigma (12 B); the noise is drawn inside the kernel
@@ -530,14 +561,21 @@ def run_ours(args):
             "launch_mode": "cuda_graph_replay" if graph is not None else "plain",
             "roofline": {"bound": "hbm", "kernel": "wigner_bwd_dg_kernel<Cfg8BP> (+ wigner_reduce_partials)", "achieved": kernels[dom]["gbs"], "peak": peak,
                          "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": traffic, "traffic_source": traffic_src,
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": abytes[dom] * micro},
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": abytes[dom] * micro,
+                         "timed": "CUDA events around every launch inside the timed region" if graph is None else
+                                  "second pass of plain launches after the graph-replayed timed region",
+                         # the same kernel alone (0.25 s idle, then 8 back-to-back launches): not power-capped
+                         "kernel_alone": {"avg_ms": round(alone_ms, 4), "gbs": round(abytes[dom] * micro / (alone_ms * 1e-3) / 1e9, 1),
+                                          "frac": round(abytes[dom] * micro / (alone_ms * 1e-3) / 1e9 / peak, 4)}},
             "pipeline_roofline": {"bytes_per_sample": 6656, "achieved_gbs": round(value / world * 6656 / 1e9, 1),
                                   "frac": round(value / world * 6656 / 1e9 / peak, 4)},
             "kernels": kernels,
-            # where a step's time goes: the four kernels' launches, summed; one rank-local step of plain launches with event
-            # records between the kernels; the timed (graph-replayed, back-to-back) step
+            # where a step's time goes: the four kernels' launches, summed (the rest is the reduction of the partial item_rep
+            # gradients, the loss terms and the packing of the all-reduce buffer); the timed step
             "step_breakdown_ms": {"sum_of_kernel_launches": round(sum(sum(v) / len(v) * (n_micro if k.startswith("wigner") else 1) for k, v in kern_ms.items()), 3),
-                                  "local_step_plain_launches": round(plain_step_ms, 3), "timed_step": round(ms_per_step, 3)},
+                                  "local_step_plain_launches_second_pass": None if plain_step_ms is None else round(plain_step_ms, 3),
+                                  "timed_step": round(ms_per_step, 3)},
+            "per_step_ms": per_step_ms if len(per_step_ms) <= 64 else per_step_ms[:64],
             "loss": loss_value, "g_item_rep_norm": g_item_norm, "e2e_loss": e2e_loss,
             # the loss is the sum of two large cancelling terms: compare runs relative to the terms, not to their difference
             "loss_terms": {"item_rep_dot_grad": loss_term_a, "log_q_dot_g_log_q": loss_value - loss_term_a},
@@ -579,7 +617,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10, help="timed steps of the end-to-end pass")
     ap.add_argument("--no-parity", action="store_true", help="skip the 4096-sample parity block against the float64 oracle")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-graph", action="store_true", help="plain launches instead of replaying a CUDA graph of the rank-local step")
+    ap.add_argument("--graph", action="store_true", help="replay a CUDA graph of the rank-local step instead of plain launches")
+    ap.add_argument("--no-graph", action="store_true", help="(default since round 2; accepted for old command lines)")
     args = ap.parse_args()
     # stdout carries exactly ONE line, the JSON result: anything a library writes to file descriptor 1 (NCCL prints its
     # version banner there) is sent to stderr, and the result goes to the saved descriptor
