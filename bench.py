@@ -434,7 +434,8 @@ def run_ours(args):
     # What a caller of the module hands over per sample is mu (36 B) and sigma (12 B); the noise is drawn inside the kernel
     # (Philox counter = global sample index: world-size independent), as the reference's module draws it itself.  Micro-batches
     # of n_loc / 8 (at most 2^20) samples through a ring of four staging buffers keep several copies in flight per rank.
-    e_micro = max(GEN_CHUNK, min(args.e2e_micro, n_loc // 8 if n_loc >= 8 * GEN_CHUNK else n_loc))
+    split = max(1, args.e2e_split)
+    e_micro = max(GEN_CHUNK, min(args.e2e_micro, n_loc // split if n_loc >= split * GEN_CHUNK else n_loc))
     while n_loc % e_micro or micro % e_micro and e_micro % micro:
         e_micro //= 2
     e_n_micro = n_loc // e_micro
@@ -453,6 +454,10 @@ def run_ours(args):
     freed = [torch.cuda.Event() for _ in range(NST)]
     out_h = torch.empty(1 + M * CHANNELS).pin_memory()
     item_p = item.clone().requires_grad_(True)
+    lq_terms = torch.empty(n_loc // GEN_CHUNK, device=dev)          # per generation chunk: sum(log_q * g_log_q), summed in float64 at the end
+    lq_prod = torch.empty(e_micro // GEN_CHUNK, GEN_CHUNK, device=dev)
+    cpg = e_micro // GEN_CHUNK
+    host_s = [0.0]
 
     def issue(i):
         b = i % NST
@@ -467,8 +472,8 @@ def run_ours(args):
         """One step; every micro-batch's mu / sigma travel host -> device inside it.  ``prefetch_next``: the copies of the NEXT
         step's first micro-batches are issued before this step's result is read back (a loader that stays one batch ahead),
         so only the first timed step pays the fill of the staging ring."""
+        t_host = time.perf_counter()
         item_p.grad = None
-        loss_acc = torch.zeros((), device=dev, dtype=torch.float64)
         main = torch.cuda.current_stream()
         if not prefetched:
             for b in range(NST):
@@ -488,7 +493,8 @@ def run_ours(args):
             # to autograd directly, exactly as a downstream module's backward would
             glq_i = glq[i * e_micro:(i + 1) * e_micro]
             torch.autograd.backward([yy, lq], [gy_for(i).view(e_micro, M, CHANNELS), glq_i.view(1, e_micro)])
-            loss_acc += (lq.detach()[0].view(-1, GEN_CHUNK) * glq_i.view(-1, GEN_CHUNK)).sum(1).double().sum()
+            torch.mul(lq.detach().view(cpg, GEN_CHUNK), glq_i.view(cpg, GEN_CHUNK), out=lq_prod)
+            torch.sum(lq_prod, 1, out=lq_terms[i * cpg:(i + 1) * cpg])
             stage[b][0].grad = None
             stage[b][1].grad = None
             stage[b][0].requires_grad_(False)
@@ -498,9 +504,10 @@ def run_ours(args):
             for i in range(min(NST - 1, e_n_micro)):
                 issue(i)
         # loss = sum(y * g_y) + sum(log_q * g_lq), with sum(y * g_y) = <item_rep, grad item_rep> (y is linear in item_rep)
-        lvdist.pack_reduction((loss_acc + (item_p.detach().double() * item_p.grad.double()).sum()).float(), item_p.grad, out=red)
+        lvdist.pack_reduction((lq_terms.double().sum() + (item_p.detach().double() * item_p.grad.double()).sum()).float(), item_p.grad, out=red)
         all_reduce_step_result()
         out_h.copy_(red, non_blocking=True)
+        host_s[0] += time.perf_counter() - t_host                  # host time to issue the step (before waiting for the GPU)
         torch.cuda.current_stream().synchronize()
         return float(out_h[0])
 
@@ -509,6 +516,7 @@ def run_ours(args):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    host_s[0] = 0.0
     for it in range(e2e_steps):
         e2e_loss = e2e_step(it > 0, it + 1 < e2e_steps)
     e1.record()
@@ -555,6 +563,7 @@ def run_ours(args):
             "e2e": {"value": samples_per_step / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
                     "h2d_bytes_per_step": n_loc * 48, "d2h_bytes_per_step": 4 * (1 + M * CHANNELS),
                     "micro_batch": e_micro, "copies_in_flight": NST - 1, "cpus_bound_to_gpu_numa_node": cpus_bound,
+                    "host_issue_ms_per_step": round(host_s[0] / e2e_steps * 1e3, 3),
                     "api": "so3_reparameterize_philox(euler) -> WignerApply (torch.autograd); pinned host mu/sigma (48 B/sample), noise "
                            "generated in the kernel; 4-deep staging ring, the next step's first copies issued before the result is read back"},
             "gpu_launches": (step_obj.LAUNCHES_PER_MICROBATCH * n_micro + step_obj.LAUNCHES_PER_SHARD) * args.steps,
@@ -615,6 +624,7 @@ def main():
     ap.add_argument("--micro", type=int, default=MICRO)
     ap.add_argument("--e2e-micro", type=int, default=1 << 20, help="largest micro-batch of the autograd-API end-to-end pass")
     ap.add_argument("--e2e-steps", type=int, default=10, help="timed steps of the end-to-end pass")
+    ap.add_argument("--e2e-split", type=int, default=8, help="micro-batches per rank and step of the end-to-end pass (if the shard allows)")
     ap.add_argument("--no-parity", action="store_true", help="skip the 4096-sample parity block against the float64 oracle")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--graph", action="store_true", help="replay a CUDA graph of the rank-local step instead of plain launches")
