@@ -15,13 +15,14 @@
 // ConvTranspose2d on this GPU under PyTorch's defaults (torch.backends.cudnn.allow_tf32 = True).  Held to the float64
 // oracle at 2e-3 relative to the output's rms (tests/test_gpu_gemm.py); the FP32-exact path stays the default.
 //
-// Anatomy (one 128 x 128 output tile per CTA, K in blocks of 32 floats = one 128-byte swizzle row, 4-stage ring):
+// Anatomy (one 128 x 256 output tile per CTA -- 24 operand bytes per MFLOP from L2 instead of the 32 of a square 128 tile, which
+// was the limit --, K in blocks of 32 floats = one 128-byte swizzle row, 4-stage ring of 16 KB A + 32 KB weight tiles):
 //   warps 0-3  A producers: 8-byte cp.async pieces (a warp covers two whole row segments) placed in the SWIZZLE_128B K-major layout by hand (rows
 //              of y are 3 240 B apart -- 8-byte, not 16-byte aligned, so TMA cannot address them), zero-filled past M and K;
-//              thread 0 also issues the TMA load of the 128 x 32 weight tile (CU_TENSOR_MAP_SWIZZLE_128B, OOB rows/cols = 0).
+//              thread 0 also issues the TMA load of the 256 x 32 weight tile (CU_TENSOR_MAP_SWIZZLE_128B, OOB rows/cols = 0).
 //              After the main loop the same warps are the epilogue: tcgen05.ld 32 lanes x 32 columns, + bias, 128-bit stores.
-//   warp 4     MMA issuer: waits full[s], one lane issues 4 x tcgen05.mma (M 128, N 128, K 8) per stage, tcgen05.commit -> empty[s];
-//              after the last block commit -> tmem_full.  Owns the TMEM allocation (128 columns).
+//   warp 4     MMA issuer: waits full[s], one lane issues 4 x tcgen05.mma (M 128, N 256, K 8) per stage, tcgen05.commit -> empty[s];
+//              after the last block commit -> tmem_full.  Owns the TMEM allocation (256 columns).
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -30,9 +31,19 @@
 
 namespace lv {
 
-constexpr int GT_BM = 128, GT_BN = 128, GT_BK = 32, GT_STAGES = 4, GT_LOOKAHEAD = 2, GT_THREADS = 160;
-constexpr uint32_t GT_TILE_BYTES = GT_BM * GT_BK * 4;          // 16 KB: 128 rows x 128 B
-constexpr size_t GT_SMEM = size_t(GT_STAGES) * 2 * GT_TILE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+#ifndef LV_GT_STAGES
+#define LV_GT_STAGES 4
+#endif
+#ifndef LV_GT_CTAS
+#define LV_GT_CTAS 1
+#endif
+#ifndef LV_GT_BN
+#define LV_GT_BN 256      // 128 x 256 output tiles: 265 TFLOP/s at 65 536 x 3 200 x 810 (128 x 128: 168; three stages: 205; cuBLAS TF32: 134)
+#endif
+constexpr int GT_BM = 128, GT_BN = LV_GT_BN, GT_BK = 32, GT_STAGES = LV_GT_STAGES, GT_LOOKAHEAD = 2, GT_THREADS = 160;
+constexpr uint32_t GT_TILE_BYTES = GT_BM * GT_BK * 4;          // A stage, 16 KB: 128 rows x 128 B
+constexpr uint32_t GT_BTILE_BYTES = GT_BN * GT_BK * 4;         // weight stage: GT_BN rows x 128 B
+constexpr size_t GT_SMEM = size_t(GT_STAGES) * (GT_TILE_BYTES + GT_BTILE_BYTES) + 1024 /* alignment slack */ + 256 /* barriers */;
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -47,7 +58,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // N >> 3 in [17,23), M >> 4 in [24,29)
 constexpr uint32_t GT_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(GT_BN >> 3) << 17) | (uint32_t(GT_BM >> 4) << 24);
 
-__global__ void __launch_bounds__(GT_THREADS, 1)
+__global__ void __launch_bounds__(GT_THREADS, LV_GT_CTAS)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_b, const float* __restrict__ A, int64_t lda, const float* __restrict__ bias,
                  int bias_div, float* __restrict__ out, int64_t ldo, int M, int N, int K) {
     extern __shared__ uint8_t smem_raw[];
@@ -55,7 +66,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_b, const float* __restri
     uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
     uint8_t* sA = smem;                                                     // [STAGES][128 rows][128 B]
     uint8_t* sB = smem + GT_STAGES * GT_TILE_BYTES;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + 2 * GT_STAGES * GT_TILE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + GT_STAGES * (GT_TILE_BYTES + GT_BTILE_BYTES));
     uint64_t* empty = full + GT_STAGES;
     uint64_t* tmem_full = empty + GT_STAGES;
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tmem_full + 1);
@@ -89,9 +100,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_b, const float* __restri
                 const int s = kb % GT_STAGES;
                 mbar_wait(empty + s, (uint32_t(kb / GT_STAGES) & 1u) ^ 1u);
                 if (tid == 0) {
-                    mbar_expect_tx(full + s, GT_TILE_BYTES);
+                    mbar_expect_tx(full + s, GT_BTILE_BYTES);
                     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                                 :: "r"(smem_u32(sB + s * GT_TILE_BYTES)), "l"(reinterpret_cast<uint64_t>(&tm_b)), "r"(kb * GT_BK), "r"(n0),
+                                 :: "r"(smem_u32(sB + s * GT_BTILE_BYTES)), "l"(reinterpret_cast<uint64_t>(&tm_b)), "r"(kb * GT_BK), "r"(n0),
                                     "r"(smem_u32(full + s)) : "memory");
                 }
                 const uint32_t dtile = smem_u32(sA + s * GT_TILE_BYTES);
@@ -176,7 +187,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_b, const float* __restri
             tc_fence_after();
             if (lane == 0) {
                 const uint64_t da = umma_desc_sw128(smem_u32(sA + s * GT_TILE_BYTES));
-                const uint64_t db = umma_desc_sw128(smem_u32(sB + s * GT_TILE_BYTES));
+                const uint64_t db = umma_desc_sw128(smem_u32(sB + s * GT_BTILE_BYTES));
 #pragma unroll
                 for (int k = 0; k < GT_BK / 8; ++k) {              // UMMA_K = 8 tf32 = 32 bytes: +2 in the (address >> 4) field
                     const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;

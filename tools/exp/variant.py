@@ -14,7 +14,9 @@ sys.path.insert(0, ROOT)
 from lie_vae_b200 import _build  # noqa: E402
 
 tag, flags = sys.argv[1], sys.argv[2:]
-srcs = ["wigner.cu"]
+srcs = ["wigner.cu"] if "--gemm" not in sys.argv else ["gemm_tf32.cu"]
+if "--gemm" in flags:
+    flags.remove("--gemm")
 if "--all" in flags:
     flags.remove("--all")
     srcs = list(_build.SOURCES)
