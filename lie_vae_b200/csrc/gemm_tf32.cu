@@ -26,24 +26,23 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
 namespace lv {
 
-#ifndef LV_GT_STAGES
-#define LV_GT_STAGES 4
-#endif
-#ifndef LV_GT_CTAS
-#define LV_GT_CTAS 1
-#endif
-#ifndef LV_GT_BN
-#define LV_GT_BN 256      // 128 x 256 output tiles: 265 TFLOP/s at 65 536 x 3 200 x 810 (128 x 128: 168; three stages: 205; cuBLAS TF32: 134)
-#endif
-constexpr int GT_BM = 128, GT_BN = LV_GT_BN, GT_BK = 32, GT_STAGES = LV_GT_STAGES, GT_LOOKAHEAD = 2, GT_THREADS = 160;
+constexpr int GT_BM = 128, GT_BK = 32, GT_STAGES = 4, GT_LOOKAHEAD = 2, GT_THREADS = 160;
 constexpr uint32_t GT_TILE_BYTES = GT_BM * GT_BK * 4;          // A stage, 16 KB: 128 rows x 128 B
-constexpr uint32_t GT_BTILE_BYTES = GT_BN * GT_BK * 4;         // weight stage: GT_BN rows x 128 B
-constexpr size_t GT_SMEM = size_t(GT_STAGES) * (GT_TILE_BYTES + GT_BTILE_BYTES) + 1024 /* alignment slack */ + 256 /* barriers */;
+// BN = 256: 265 TFLOP/s at 65 536 x 3 200 x 810 (BN = 128: 168; BN = 256 with three stages: 205; cuBLAS TF32: 133); BN = 128 is kept
+// for problems too small to fill the SMs with 256-wide tiles (lv_gemm_tf32_f32 chooses)
+template <int BN> struct GtGeo {
+    static constexpr uint32_t BTILE_BYTES = BN * GT_BK * 4;     // weight stage: BN rows x 128 B
+    static constexpr size_t SMEM = size_t(GT_STAGES) * (GT_TILE_BYTES + BTILE_BYTES) + 1024 /* alignment slack */ + 256 /* barriers */;
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10), both K-major,
+    // N >> 3 in [17,23), M >> 4 in [24,29)
+    static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(GT_BM >> 4) << 24);
+};
 
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -54,13 +53,11 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return uint64_t((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
 }
-// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (1 << 4), A = B = TF32 (2 << 7, 2 << 10), both K-major,
-// N >> 3 in [17,23), M >> 4 in [24,29)
-constexpr uint32_t GT_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(GT_BN >> 3) << 17) | (uint32_t(GT_BM >> 4) << 24);
-
-__global__ void __launch_bounds__(GT_THREADS, LV_GT_CTAS)
+template <int GT_BN>
+__global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tm_b, const float* __restrict__ A, int64_t lda, const float* __restrict__ bias,
                  int bias_div, float* __restrict__ out, int64_t ldo, int M, int N, int K) {
+    constexpr uint32_t GT_BTILE_BYTES = GtGeo<GT_BN>::BTILE_BYTES, GT_IDESC = GtGeo<GT_BN>::IDESC;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;            // swizzle atoms are 1024-byte aligned
     uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -255,10 +252,15 @@ extern "C" int lv_gemm_tf32_f32(const float* A, int64_t lda, const float* Bt, in
     if ((reinterpret_cast<uintptr_t>(Bt) & 15u) || (ldb & 3)) { lv::set_error("gemm_tf32: Bt must be 16-byte aligned with a row stride that is a multiple of 4 floats"); return LV_ERR_ALIGN; }
     lv::EncodeTiledFn enc = lv::encode_tiled_fn();
     if (!enc) { lv::set_error("gemm_tf32: cuTensorMapEncodeTiled is not available from this driver"); return LV_ERR_UNSUPPORTED; }
+    // tile width: 256 unless that leaves most SMs without a tile while 128-wide tiles would not (small dgrad-shaped problems)
+    const int64_t mt = (M + lv::GT_BM - 1) / lv::GT_BM;
+    int bn = 256;
+    if (mt * ((N + 255) / 256) < 64 && N > 128) bn = 128;
+    if (const char* e = getenv("LV_GEMM_BN")) { if (atoi(e) == 128 || atoi(e) == 256) bn = atoi(e); }     // A/B runs
     CUtensorMap tm;
     const cuuint64_t gdim[2] = {cuuint64_t(K), cuuint64_t(N)};
     const cuuint64_t gstride[1] = {cuuint64_t(ldb) * 4};
-    const cuuint32_t box[2] = {cuuint32_t(lv::GT_BK), cuuint32_t(lv::GT_BN)};
+    const cuuint32_t box[2] = {cuuint32_t(lv::GT_BK), cuuint32_t(bn)};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(Bt), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -267,12 +269,17 @@ extern "C" int lv_gemm_tf32_f32(const float* A, int64_t lda, const float* Bt, in
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !opted[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(lv::gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(lv::GT_SMEM));
+        cudaError_t e = cudaFuncSetAttribute(lv::gemm_tf32_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(lv::GtGeo<256>::SMEM));
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(lv::gemm_tf32_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(lv::GtGeo<128>::SMEM));
         if (e != cudaSuccess) { lv::set_error("gemm_tf32: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return int(e); }
         opted[dev] = true;
     }
-    const int64_t tiles = ((N + lv::GT_BN - 1) / lv::GT_BN) * ((M + lv::GT_BM - 1) / lv::GT_BM);
+    const int64_t tiles = ((N + bn - 1) / bn) * mt;
     if (tiles > 0x7fffffffLL) { lv::set_error("gemm_tf32: too many tiles"); return LV_ERR_ARG; }
-    lv::gemm_tf32_kernel<<<unsigned(tiles), lv::GT_THREADS, lv::GT_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tm, A, lda, bias, bias_div, out, ldo, int(M), N, K);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (bn == 256)
+        lv::gemm_tf32_kernel<256><<<unsigned(tiles), lv::GT_THREADS, lv::GtGeo<256>::SMEM, st>>>(tm, A, lda, bias, bias_div, out, ldo, int(M), N, K);
+    else
+        lv::gemm_tf32_kernel<128><<<unsigned(tiles), lv::GT_THREADS, lv::GtGeo<128>::SMEM, st>>>(tm, A, lda, bias, bias_div, out, ldo, int(M), N, K);
     return lv::check_launch("gemm_tf32");
 }
