@@ -680,6 +680,10 @@ def gemm_tf32(a, bt, bias=None, bias_div=1, out=None):
 
 
 ACTION_GEMM_CHUNK = 8192      # samples per chunk: y of a chunk (3 240 B/sample for l <= 8, C = 10) stays L2-resident
+# The weight gradient y^T g_out of the fused op is a cuBLAS call (its operands are MN-major for the tcgen05 kernel above).  True: TF32
+# operands there too -- what cuDNN does for the reference's ConvTranspose2d weight gradient under PyTorch's defaults, and what
+# the forward and the data gradient of this op use; False: FP32 (twice the time: 64 vs 133 TFLOP/s).
+ACTION_GEMM_WGRAD_TF32 = True
 
 
 class ActionGemm(Function):
@@ -691,7 +695,7 @@ class ActionGemm(Function):
     stays in L2: per chunk the Wigner forward kernel writes y into a reused buffer and the tcgen05 TF32 GEMM reads it back
     from L2; y never round-trips through HBM and is not kept for the backward, which recomputes it per chunk, runs the
     data gradient g_y = g_out W^T on the same tcgen05 kernel (TF32, like cuDNN's default for the reference's convolution),
-    feeds it from L2 straight into the Wigner backward kernel, and leaves the weight gradient y^T g_out to cuBLAS (FP32).
+    feeds it from L2 straight into the Wigner backward kernel, and leaves the weight gradient y^T g_out to cuBLAS (TF32 operands by default, ACTION_GEMM_WGRAD_TF32).
     """
 
     @staticmethod
@@ -747,7 +751,12 @@ class ActionGemm(Function):
                 n = min(chunk, N - lo)
                 gc = g[lo:lo + n]
                 _cabi.call("lv_wigner_apply_fwd_f32", _cabi.ptr(a_c[lo:lo + n]), _cabi.ptr(s_c), _cabi.ptr(ybuf), n, 0, lmax, C, 1, int(transpose), st)
-                gw.addmm_(ybuf[:n].t(), gc)                                  # wgrad (cuBLAS), y from L2
+                prev_tf32 = torch.backends.cuda.matmul.allow_tf32
+                torch.backends.cuda.matmul.allow_tf32 = bool(ACTION_GEMM_WGRAD_TF32)
+                try:
+                    gw.addmm_(ybuf[:n].t(), gc)                              # wgrad (cuBLAS), y from L2
+                finally:
+                    torch.backends.cuda.matmul.allow_tf32 = prev_tf32
                 # dgrad on the tensor cores too: g_y = g_out (n, Nout) @ W^T -- W (K, Nout) is already the K-major "Bt" of this
                 # product; g_y stays in L2 for the Wigner backward
                 if w_r is not None:

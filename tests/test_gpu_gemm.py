@@ -53,13 +53,17 @@ def test_gemm_tf32_vs_float64(mods, M, N, K):
     assert torch.equal(_ops.gemm_tf32(ai, bi[:, :K]), (ai.double() @ bi[:, :K].double().t()).float())
 
 
+@pytest.mark.parametrize("wgrad_tf32", [True, False])
 @pytest.mark.parametrize("L,Nout,div,N,tr,chunk", [(8, 800, 16, 1000, False, 8192), (6, 3200, 16, 1024, False, 300), (4, 50, 1, 777, True, 8192),
                                                    (8, 384, 16, 20001, False, 8192)])
-def test_action_gemm_function_vs_float64(mods, L, Nout, div, N, tr, chunk):
-    """ActionGemm (chunked Wigner forward -> tcgen05 GEMM; backward: recompute, cuBLAS dgrad / wgrad, Wigner backward) against
-    float64 autograd of oracle-action @ weight + bias.  The output and the gradients that flow through the data-gradient GEMM
-    (g_angles, g_item_rep) are TF32-accurate; the weight / bias gradients (cuBLAS FP32 on the recomputed y) FP32-accurate."""
+def test_action_gemm_function_vs_float64(mods, L, Nout, div, N, tr, chunk, wgrad_tf32, monkeypatch):
+    """ActionGemm (chunked Wigner forward -> tcgen05 GEMM; backward: recompute, tcgen05 dgrad, cuBLAS wgrad, Wigner backward)
+    against float64 autograd of oracle-action @ weight + bias.  The output and the gradients that flow through the data-gradient
+    GEMM (g_angles, g_item_rep) are TF32-accurate; the weight gradient is TF32-accurate by default (ACTION_GEMM_WGRAD_TF32, cuDNN's
+    default for the reference's layer) and FP32-accurate with the switch off; the bias gradient is FP32."""
     _ops, _ = mods
+    monkeypatch.setattr(_ops, "ACTION_GEMM_WGRAD_TF32", wgrad_tf32)
+    allow_before = torch.backends.cuda.matmul.allow_tf32
     torch.manual_seed(L + Nout)
     C = 10
     Mh = (L + 1) ** 2
@@ -76,8 +80,9 @@ def test_action_gemm_function_vs_float64(mods, L, Nout, div, N, tr, chunk):
     (out * gw.float().cuda()).sum().backward()
     assert rel_rms(out, out64.detach()) < TF32_TOL
     for got, want, what, tol in ((a.grad, ang64.grad, "g_angles", TF32_TOL), (it.grad, it64.grad, "g_item_rep", TF32_TOL),
-                                 (w.grad, w64.grad, "g_weight", 1e-4), (b.grad, b64.grad, "g_bias", 1e-4)):
+                                 (w.grad, w64.grad, "g_weight", TF32_TOL if wgrad_tf32 else 1e-4), (b.grad, b64.grad, "g_bias", 1e-4)):
         assert rel_rms(got, want) < tol, what
+    assert torch.backends.cuda.matmul.allow_tf32 == allow_before          # the global switch is restored
 
 
 @pytest.mark.parametrize("kind,L,hidden,N", [("deconv", 8, 50, 1000), ("deconv", 6, 200, 1024), ("mlp", 4, 0, 777)])
