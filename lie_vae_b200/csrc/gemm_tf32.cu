@@ -252,10 +252,11 @@ extern "C" int lv_gemm_tf32_f32(const float* A, int64_t lda, const float* Bt, in
     if ((reinterpret_cast<uintptr_t>(Bt) & 15u) || (ldb & 3)) { lv::set_error("gemm_tf32: Bt must be 16-byte aligned with a row stride that is a multiple of 4 floats"); return LV_ERR_ALIGN; }
     lv::EncodeTiledFn enc = lv::encode_tiled_fn();
     if (!enc) { lv::set_error("gemm_tf32: cuTensorMapEncodeTiled is not available from this driver"); return LV_ERR_UNSUPPORTED; }
-    // tile width: 256 unless that leaves most SMs without a tile while 128-wide tiles would not (small dgrad-shaped problems)
+    // tile width: 256 unless the output is at most 128 columns wide or 256-wide tiles would leave most SMs without a tile (small
+    // dgrad-shaped problems)
     const int64_t mt = (M + lv::GT_BM - 1) / lv::GT_BM;
     int bn = 256;
-    if (mt * ((N + 255) / 256) < 64 && N > 128) bn = 128;
+    if (N <= 128 || mt * ((N + 255) / 256) < 64) bn = 128;
     if (const char* e = getenv("LV_GEMM_BN")) { if (atoi(e) == 128 || atoi(e) == 256) bn = atoi(e); }     // A/B runs
     CUtensorMap tm;
     const cuuint64_t gdim[2] = {cuuint64_t(K), cuuint64_t(N)};
